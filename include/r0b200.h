@@ -1,0 +1,123 @@
+/* r0b200 — C ABI of the B200-native (sm_100a) backend for the RISC Zero STARK prover hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types. Each entry point replaces one
+ * method of the reference `risc0_zkp::hal::Hal` trait (risc0/zkp/src/hal/mod.rs:55-258), of `CircuitHal`
+ * (hal/mod.rs:265-290), or one symbol of the reference's existing FFI tables
+ * (`risc0_zkp_cuda_*`: risc0/sys/kernels/zkp/cuda/ffi.cu:25-145, `sppark_*`: risc0/sys/src/cuda.rs:19-80,
+ * `risc0_circuit_rv32im_cuda_eval_check`: risc0/circuit/rv32im-sys/src/lib.rs:87-133). INTEGRATION.md shows the Rust
+ * `impl Hal for B200Hal` that binds them.
+ *
+ * Conventions
+ *  - Error convention is the reference's (risc0/sys/src/lib.rs:53-75): every call returns `const char*`; NULL means
+ *    success, otherwise a heap string the caller releases with r0b200_free_error() (libc free works too).
+ *  - All `uint32_t*` buffers are DEVICE pointers unless the parameter name ends in `_host`. Field elements are
+ *    BabyBear Montgomery words exactly as in the reference's Buffer<Elem> (canonical, < P, or 0xffffffff = INVALID);
+ *    extension elements are 4 consecutive words; digests are 8 words. Matrices are column-major: buf[col*rows + row].
+ *  - Work is stream-ordered on the context's stream and returns without waiting for the GPU (the reference's CudaHal
+ *    blocks on every call, hal/cuda.rs + cuda.h:77-100). Results are visible to the host after r0b200_copy_d2h()
+ *    (which synchronises, like Buffer::view / get_at) or r0b200_sync().
+ *  - One context = one device ordinal + one stream + one prover at a time (the reference hard-codes device 0,
+ *    hal/cuda.rs:406); contexts on different devices are independent, which is how segments shard across GPUs.
+ */
+#ifndef R0B200_H
+#define R0B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct r0b200_ctx r0b200_ctx;
+typedef const char* r0b200_err;
+
+enum { R0B200_HASH_POSEIDON2 = 0, R0B200_HASH_SHA256 = 1 };
+
+/* ---- context (CudaHal::new_from_hash, hal/cuda.rs:397-421; sppark_init, supra/ntt.cu:4-32) ---- */
+r0b200_err r0b200_create(int device, r0b200_ctx** out);
+void r0b200_destroy(r0b200_ctx* ctx);
+void r0b200_free_error(const char* err);
+r0b200_err r0b200_sync(r0b200_ctx* ctx);
+void* r0b200_stream(r0b200_ctx* ctx);              /* the cudaStream_t, for callers that enqueue their own work */
+uint64_t r0b200_launch_count(r0b200_ctx* ctx);     /* kernels launched so far through this context */
+uint64_t r0b200_bytes_peak(r0b200_ctx* ctx);       /* MemoryTracker.peak analogue, hal/mod.rs:297-317 */
+/* CUDA-event timer on the context's stream (the stream the kernels are launched on): start records an event, stop
+ * records a second one, waits for it and returns the elapsed device time in milliseconds. */
+r0b200_err r0b200_timer_start(r0b200_ctx* ctx);
+r0b200_err r0b200_timer_stop(r0b200_ctx* ctx, float* ms);
+
+/* ---- buffers (Hal::alloc_* / copy_from_* hal/mod.rs:67-100; Buffer::view/get_at/view_mut hal/mod.rs:39-53) ---- */
+r0b200_err r0b200_alloc(r0b200_ctx* ctx, size_t bytes, void** dptr);
+r0b200_err r0b200_free(r0b200_ctx* ctx, void* dptr);
+r0b200_err r0b200_copy_h2d(r0b200_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+r0b200_err r0b200_copy_d2h(r0b200_ctx* ctx, void* dst_host, const void* src, size_t bytes); /* synchronises */
+r0b200_err r0b200_fill_u32(r0b200_ctx* ctx, uint32_t* dst, uint32_t word, size_t count);   /* alloc_elem_init */
+
+/* ---- NTT family ---- */
+/* Hal::batch_interpolate_ntt (cpu.rs:342-350; sppark_batch_iNTT): `count` rows of 2^lg_n, in place;
+ * natural-order values in, bit-reversed coefficients out, scaled by 2^-lg_n. */
+r0b200_err r0b200_batch_interpolate_ntt(r0b200_ctx* ctx, uint32_t* io, size_t count, uint32_t lg_n);
+/* Fused make_coeffs tail (prove/prover.rs:38-48): batch_interpolate_ntt followed by zk_shift in one pass. */
+r0b200_err r0b200_batch_interpolate_ntt_zk(r0b200_ctx* ctx, uint32_t* io, size_t count, uint32_t lg_n);
+/* Hal::zk_shift (cpu.rs:395-408; sppark_batch_zk_shift): io[p*n + i] *= 3^brev(i). */
+r0b200_err r0b200_zk_shift(r0b200_ctx* ctx, uint32_t* io, size_t count, uint32_t lg_n);
+/* Hal::batch_expand_into_evaluate_ntt (cpu.rs:305-340; sppark_batch_expand + sppark_batch_NTT): rows of
+ * 2^lg_in bit-reversed coefficients -> rows of 2^(lg_in+expand_bits) natural-order evaluations. expand_bits in {0, 2}. */
+r0b200_err r0b200_batch_expand_into_evaluate_ntt(r0b200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count,
+                                                 uint32_t lg_in, uint32_t expand_bits);
+/* Hal::batch_bit_reverse (cpu.rs:352-360; risc0_zkp_cuda_batch_bit_reverse). */
+r0b200_err r0b200_batch_bit_reverse(r0b200_ctx* ctx, uint32_t* io, size_t count, uint32_t lg_n);
+
+/* ---- hashing / Merkle ---- */
+/* Hal::hash_rows (cpu.rs:555-567; sppark_poseidon2_rows / risc0_zkp_cuda_sha_rows): out[r] = H(matrix[:, r]). */
+r0b200_err r0b200_hash_rows(r0b200_ctx* ctx, int hash, uint32_t* out_digests, const uint32_t* matrix, size_t rows,
+                            size_t cols);
+/* Hal::hash_fold (cpu.rs:569-581; sppark_poseidon2_fold / risc0_zkp_cuda_sha_fold): one heap level. */
+r0b200_err r0b200_hash_fold(r0b200_ctx* ctx, int hash, uint32_t* io_digests, size_t input_size, size_t output_size);
+/* MerkleTreeProver::new (prove/merkle.rs:54-81) in one call: nodes[rows..2*rows) = hash_rows, then every fold level;
+ * nodes has 2*rows digests. */
+r0b200_err r0b200_merkle_build(r0b200_ctx* ctx, int hash, uint32_t* nodes, const uint32_t* matrix, size_t rows,
+                               size_t cols);
+
+/* ---- element-wise / FRI / mixing ---- */
+r0b200_err r0b200_eltwise_add_elem(r0b200_ctx* ctx, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n);
+r0b200_err r0b200_eltwise_copy_elem(r0b200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t n);
+r0b200_err r0b200_eltwise_zeroize_elem(r0b200_ctx* ctx, uint32_t* io, size_t n);
+/* Hal::eltwise_sum_extelem (cpu.rs:475-500): in = to_add x count AoS ext elems -> out = 4 SoA planes of count. */
+r0b200_err r0b200_eltwise_sum_extelem(r0b200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t to_add);
+/* Hal::eltwise_copy_elem_slice (cpu.rs:617-635): strided copy from a HOST slice. */
+r0b200_err r0b200_eltwise_copy_elem_slice(r0b200_ctx* ctx, uint32_t* into, const uint32_t* from_host, size_t from_rows,
+                                          size_t from_cols, size_t from_offset, size_t from_stride, size_t into_offset,
+                                          size_t into_stride);
+/* Hal::fri_fold (cpu.rs:524-553): out = 4 planes of count; in = 4 planes of 16*count; mix = 4 host words. */
+r0b200_err r0b200_fri_fold(r0b200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, const uint32_t* mix_host);
+/* Hal::mix_poly_coeffs (cpu.rs:410-455): out (ext, combos x count) += mix_start*mix^i * in[i] for column i.
+ * combos_host: combo id per input column (the reference passes it as a device u32 buffer built from host data). */
+r0b200_err r0b200_mix_poly_coeffs(r0b200_ctx* ctx, uint32_t* out, const uint32_t* mix_start_host,
+                                  const uint32_t* mix_host, const uint32_t* in, const uint32_t* combos_host,
+                                  size_t input_size, size_t count);
+/* Hal::batch_evaluate_any (cpu.rs:362-393): out[e] = sum_i coeffs[which[e]*n + i] * xs[e]^i ; which/xs/out on device. */
+r0b200_err r0b200_batch_evaluate_any(r0b200_ctx* ctx, const uint32_t* coeffs, size_t poly_count, uint32_t lg_n,
+                                     const uint32_t* which, const uint32_t* xs, uint32_t* out, size_t eval_count);
+/* Hal::gather_sample (cpu.rs:583-596). */
+r0b200_err r0b200_gather_sample(r0b200_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size,
+                                size_t stride);
+/* Hal::scatter (cpu.rs:598-615): CSR scatter from HOST index/offsets/values. */
+r0b200_err r0b200_scatter(r0b200_ctx* ctx, uint32_t* into, const uint32_t* index_host, size_t index_len,
+                          const uint32_t* offsets_host, const uint32_t* values_host);
+/* Hal::prefix_products (cpu.rs:637-642). */
+r0b200_err r0b200_prefix_products(r0b200_ctx* ctx, uint32_t* io_ext, size_t n);
+/* Hal::combos_prepare (hal/mod.rs:202-234). */
+r0b200_err r0b200_combos_prepare(r0b200_ctx* ctx, uint32_t* combos, const uint32_t* coeff_u_host, size_t coeff_u_len,
+                                 uint32_t combo_count, size_t cycles, const uint32_t* reg_sizes_host,
+                                 const uint32_t* reg_combo_ids_host, uint32_t nregs, const uint32_t* mix_host);
+/* Hal::combos_divide (hal/mod.rs:236-257): chunk i (cycles ext elems) is divided in place by (x - pows[k]) for
+ * k in [pow_begin[i], pow_begin[i+1]). Fails if any remainder is non-zero (the reference asserts). Synchronises. */
+r0b200_err r0b200_combos_divide(r0b200_ctx* ctx, uint32_t* combos, size_t nchunks, const uint32_t* pow_begin_host,
+                                const uint32_t* pows_host, size_t cycles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R0B200_H */

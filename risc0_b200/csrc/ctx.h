@@ -1,0 +1,75 @@
+// Internal context shared by the kernels' host launchers (not part of the public C ABI; see include/r0b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "fp.cuh"
+
+namespace r0 {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define R0_CUDA(expr)                                                                                     \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      throw r0::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                          std::to_string(__LINE__) + ")");                                                \
+  } while (0)
+
+#define R0_CHECK(cond, msg)                                 \
+  do {                                                      \
+    if (!(cond)) throw std::invalid_argument(std::string(msg)); \
+  } while (0)
+
+constexpr int MAX_LG = 24;  // largest supported NTT size 2^24 (MAX_CYCLES_PO2 = 22 -> 4N = 2^24, zkp/src/lib.rs:35-38)
+
+struct Tables {
+  // two-level twiddle tables for the order-2^24 roots: w^E = hi[E >> 12] * lo[E & 4095]; dir 0 = ROU_REV, 1 = ROU_FWD
+  uint32_t* tw_lo[2];
+  uint32_t* tw_hi[2];
+  // powers of three, same two-level split: 3^e = p3_hi[e >> 12] * p3_lo[e & 4095]
+  uint32_t* p3_lo;
+  uint32_t* p3_hi;
+  // (2^k)^-1 * 3^(4096 j), lazily built per k ; and plain (2^k)^-1
+  uint32_t* p3_hi_scaled[MAX_LG + 1];
+  uint32_t ninv[MAX_LG + 1];
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  Tables tab{};
+  uint64_t launches = 0;       // kernels launched through this context (bench.py's gpu_launches)
+  size_t bytes_allocated = 0;  // MemoryTracker analogue (hal/mod.rs:292-317)
+  size_t bytes_peak = 0;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+};
+
+inline void count_launch(Ctx* c, uint64_t n = 1) { c->launches += n; }
+
+}  // namespace r0
+
+// The opaque handle of the C ABI.
+struct r0b200_ctx : r0::Ctx {};
+
+// C ABI error convention (same as risc0/sys/src/lib.rs:53-75): NULL = success, otherwise a strdup'd message the
+// caller releases with r0b200_free_error / libc free. C++ exceptions never cross the boundary.
+#define R0_API_BEGIN try {
+#define R0_API_END                       \
+  }                                      \
+  catch (const std::exception& e) {      \
+    return strdup(e.what());             \
+  }                                      \
+  catch (...) {                          \
+    return strdup("unknown C++ exception"); \
+  }                                      \
+  return nullptr;

@@ -1,0 +1,41 @@
+// Host-side launcher prototypes (one per kernel family). Internal to libr0b200.so.
+#pragma once
+#include "ctx.h"
+
+void r0_ntt_init_tables(r0::Ctx* c);
+void r0_ntt_free_tables(r0::Ctx* c);
+void r0_ntt_interpolate(r0::Ctx* c, uint32_t* io, size_t count, int k, bool zk, size_t cols_per_launch);
+void r0_ntt_expand_evaluate(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t count, int k, int eb,
+                            size_t cols_per_launch);
+void r0_bit_reverse(r0::Ctx* c, uint32_t* io, size_t count, int k);
+
+void r0_poseidon2_init(r0::Ctx* c);
+void r0_p2_hash_rows(r0::Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols);
+void r0_p2_hash_fold(r0::Ctx* c, uint32_t* io, size_t in_size, size_t out_size);
+void r0_p2_merkle_fold_all(r0::Ctx* c, uint32_t* nodes, size_t leaves);
+void r0_sha_hash_rows(r0::Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols);
+void r0_sha_hash_fold(r0::Ctx* c, uint32_t* io, size_t in_size, size_t out_size);
+
+void r0_eltwise_add(r0::Ctx* c, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n);
+void r0_eltwise_copy(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t n);
+void r0_eltwise_zeroize(r0::Ctx* c, uint32_t* io, size_t n);
+void r0_fill(r0::Ctx* c, uint32_t* io, uint32_t v, size_t n);
+void r0_eltwise_sum_ext(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t count, size_t to_add);
+void r0_zk_shift(r0::Ctx* c, uint32_t* io, size_t count, int bits);
+void r0_fri_fold(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t count, const r0::FpExt& mix);
+void r0_mix_poly_coeffs(r0::Ctx* c, uint32_t* out, const r0::FpExt& mix_start, const r0::FpExt& mix, const uint32_t* in,
+                        const uint32_t* combos_host, size_t input_size, size_t count);
+void r0_batch_evaluate_any(r0::Ctx* c, const uint32_t* coeffs, size_t n, const uint32_t* which_dev,
+                           const uint32_t* xs_dev, uint32_t* out_dev, size_t eval_count);
+void r0_gather_sample(r0::Ctx* c, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride);
+void r0_scatter(r0::Ctx* c, uint32_t* into, const uint32_t* index_host, size_t index_len, const uint32_t* offsets_host,
+                const uint32_t* values_host);
+void r0_copy_elem_slice(r0::Ctx* c, uint32_t* into, const uint32_t* from_host, size_t from_rows, size_t from_cols,
+                        size_t from_offset, size_t from_stride, size_t into_offset, size_t into_stride);
+void r0_prefix_products(r0::Ctx* c, uint32_t* io, size_t n);
+void r0_combos_prepare(r0::Ctx* c, uint32_t* combos, const r0::FpExt* coeff_u_host, size_t coeff_u_len,
+                       uint32_t combo_count, size_t cycles, const uint32_t* reg_sizes, const uint32_t* reg_combo_ids,
+                       uint32_t nregs, const r0::FpExt& mix, uint32_t check_size);
+void r0_poly_divide(r0::Ctx* c, uint32_t* poly, size_t n, const r0::FpExt& z, uint32_t* remainder_dev);
+void r0_gather_batched(r0::Ctx* c, uint32_t* dst, const void* jobs_host, size_t njobs);
+void r0_gather_digests(r0::Ctx* c, uint32_t* dst, const void* jobs_host, size_t njobs);

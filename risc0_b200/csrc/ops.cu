@@ -1,0 +1,512 @@
+// Element-wise, FRI, coefficient-mixing, evaluation, division and gather kernels of the Hal trait, sm_100a.
+//
+// Replaces (reference CPU spec -> reference CUDA kernel):
+//   eltwise_add/copy/zeroize/sum   cpu.rs:457-522        -> risc0/sys/kernels/zkp/cuda/eltwise.cu:18-86
+//   fri_fold                       cpu.rs:524-553        -> kernels.cu:74-93
+//   mix_poly_coeffs                cpu.rs:410-455        -> kernels.cu:116-132 (serial RMW loop per thread)
+//   batch_evaluate_any             cpu.rs:362-393        -> kernels.cu:46-72   (one block per evaluation)
+//   gather_sample / scatter        cpu.rs:583-615        -> kernels.cu:95-114
+//   combos_prepare / combos_divide hal/mod.rs:202-257    -> combos.cu:17-51, sppark div_by_x_minus_z
+//   prefix_products, eltwise_copy_elem_slice cpu.rs:617-642
+// All of these are HBM-bound streaming kernels: grid-stride loops sized to a multiple of the SM count, 32-bit
+// coalesced or 128-bit vector accesses, products accumulated lazily in 64 bits (fp.cuh lazy_mac) so an
+// FpExt += Fp * FpExt costs four IMAD.WIDE instead of four full Montgomery products.
+#include "ctx.h"
+
+namespace r0 {
+
+static inline unsigned grid_for(const Ctx* c, size_t n, int block = 256, int waves = 8) {
+  size_t blocks = (n + block - 1) / block;
+  size_t cap = (size_t)c->sm_count * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+#define GRID_STRIDE(i, n) for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
+
+__global__ void k_add(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) {
+  GRID_STRIDE(i, n) out[i] = fp_add(a[i], b[i]);
+}
+__global__ void k_copy(uint32_t* out, const uint32_t* in, size_t n) { GRID_STRIDE(i, n) out[i] = in[i]; }
+__global__ void k_copy4(uint4* out, const uint4* in, size_t n4) { GRID_STRIDE(i, n4) out[i] = in[i]; }
+__global__ void k_zeroize(uint32_t* io, size_t n) {
+  GRID_STRIDE(i, n) {
+    uint32_t v = io[i];
+    if (v == FP_INVALID) io[i] = 0;
+  }
+}
+__global__ void k_fill(uint32_t* io, uint32_t v, size_t n) { GRID_STRIDE(i, n) io[i] = v; }
+
+// in: to_add x count AoS FpExt ; out: 4 SoA planes of count
+__global__ void k_sum_ext(uint32_t* out, const uint4* in, size_t count, size_t to_add) {
+  GRID_STRIDE(i, count) {
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (size_t t = 0; t < to_add; t++) {
+      uint4 v = in[t * count + i];
+      s0 = fp_add(s0, v.x);
+      s1 = fp_add(s1, v.y);
+      s2 = fp_add(s2, v.z);
+      s3 = fp_add(s3, v.w);
+    }
+    out[i] = s0;
+    out[count + i] = s1;
+    out[2 * count + i] = s2;
+    out[3 * count + i] = s3;
+  }
+}
+
+// out[k*count + idx] = (sum_{i<16} mix^i * in_ext[brev4(i)*count + idx])[k], in_ext component j at in[j*16*count + ..]
+__global__ void k_fri_fold(uint32_t* out, const uint32_t* in, size_t count, const FpExt* mix_pows /*16*/) {
+  __shared__ FpExt mp[16];
+  if (threadIdx.x < 16) mp[threadIdx.x] = mix_pows[threadIdx.x];
+  __syncthreads();
+  GRID_STRIDE(idx, count) {
+    FpExt tot = ext_zero();
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int rev = ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3);
+      const size_t p = (size_t)rev * count + idx;
+      FpExt f{{in[p], in[16 * count + p], in[32 * count + p], in[48 * count + p]}};
+      tot = ext_add(tot, ext_mul(mp[i], f));
+    }
+    out[idx] = tot.c[0];
+    out[count + idx] = tot.c[1];
+    out[2 * count + idx] = tot.c[2];
+    out[3 * count + idx] = tot.c[3];
+  }
+}
+
+// One pass over the input columns: columns are pre-sorted by combo id on the host (`order`), each thread owns one
+// coefficient index and accumulates every combo in registers, then does ONE read-modify-write per touched combo.
+//   out[combo*count + idx] += sum_{i in combo} mix_pows[i] * in[i*count + idx]
+__global__ void k_mix_poly_coeffs(uint4* out, const uint32_t* in, size_t count, const uint32_t* order /*input_size*/,
+                                  const uint32_t* seg_begin /*nseg+1*/, const uint32_t* seg_combo /*nseg*/,
+                                  uint32_t nseg, const FpExt* mix_pows /*input_size, indexed by column*/) {
+  GRID_STRIDE(idx, count) {
+    for (uint32_t s = 0; s < nseg; s++) {
+      uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (uint32_t q = seg_begin[s]; q < seg_begin[s + 1]; q++) {
+        const uint32_t col = order[q];
+        const uint32_t v = in[(size_t)col * count + idx];
+        const uint4 m = *reinterpret_cast<const uint4*>(&mix_pows[col]);
+        lazy_mac(a0, v, m.x);
+        lazy_mac(a1, v, m.y);
+        lazy_mac(a2, v, m.z);
+        lazy_mac(a3, v, m.w);
+      }
+      uint4* o = out + (size_t)seg_combo[s] * count + idx;
+      uint4 cur = *o;
+      cur.x = fp_add(cur.x, lazy_finish(a0));
+      cur.y = fp_add(cur.y, lazy_finish(a1));
+      cur.z = fp_add(cur.z, lazy_finish(a2));
+      cur.w = fp_add(cur.w, lazy_finish(a3));
+      *o = cur;
+    }
+  }
+}
+
+// ---- batch_evaluate_any -------------------------------------------------------------------------------------
+// out[e] = sum_i coeffs[which[e]*n + i] * xs[e]^i. Block (chunk, e): 256 threads x CH coefficients each;
+// thread t takes i = base + j*256 + t, so sum = x^base * sum_t x^t * sum_j c[..] * (x^256)^j. The powers x^t and
+// (x^256)^j come from per-evaluation tables built by k_eval_tables; partial sums go to `partial[e][chunk]`.
+constexpr int EV_T = 256;
+constexpr int EV_CH = 32;  // coefficients per thread -> 8192 per block
+
+__global__ void k_eval_tables(FpExt* xt /*[E][256]*/, FpExt* xq /*[E][EV_CH]*/, FpExt* xc /*[E][nchunks]*/,
+                              const FpExt* xs, int nchunks) {
+  const int e = blockIdx.x;
+  const FpExt x = xs[e];
+  const int t = threadIdx.x;
+  xt[(size_t)e * EV_T + t] = ext_pow(x, t);
+  const FpExt x256 = ext_pow(x, EV_T);
+  if (t < EV_CH) xq[(size_t)e * EV_CH + t] = ext_pow(x256, t);
+  const FpExt xblk = ext_pow(x256, EV_CH);
+  for (int c = t; c < nchunks; c += blockDim.x) xc[(size_t)e * nchunks + c] = ext_pow(xblk, c);
+}
+
+__global__ void __launch_bounds__(EV_T) k_eval_partial(FpExt* partial, const uint32_t* coeffs, size_t n,
+                                                       const uint32_t* which, const FpExt* xt, const FpExt* xq,
+                                                       const FpExt* xc, int nchunks) {
+  __shared__ FpExt q[EV_CH];
+  __shared__ FpExt red[EV_T];
+  const int e = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+  if (t < EV_CH) q[t] = xq[(size_t)e * EV_CH + t];
+  __syncthreads();
+  const uint32_t* poly = coeffs + (size_t)which[e] * n;
+  const size_t base = (size_t)chunk * EV_T * EV_CH;
+  uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 8
+  for (int j = 0; j < EV_CH; j++) {
+    const size_t i = base + (size_t)j * EV_T + t;
+    const uint32_t c = i < n ? poly[i] : 0u;
+    lazy_mac(a0, c, q[j].c[0]);
+    lazy_mac(a1, c, q[j].c[1]);
+    lazy_mac(a2, c, q[j].c[2]);
+    lazy_mac(a3, c, q[j].c[3]);
+  }
+  FpExt s{{lazy_finish(a0), lazy_finish(a1), lazy_finish(a2), lazy_finish(a3)}};
+  red[t] = ext_mul(s, xt[(size_t)e * EV_T + t]);
+  __syncthreads();
+  for (int w = EV_T / 2; w > 0; w >>= 1) {
+    if (t < w) red[t] = ext_add(red[t], red[t + w]);
+    __syncthreads();
+  }
+  if (t == 0) partial[(size_t)e * nchunks + chunk] = ext_mul(red[0], xc[(size_t)e * nchunks + chunk]);
+}
+
+__global__ void k_eval_final(FpExt* out, const FpExt* partial, int nchunks) {
+  __shared__ FpExt red[256];
+  const int e = blockIdx.x, t = threadIdx.x;
+  FpExt s = ext_zero();
+  for (int c = t; c < nchunks; c += blockDim.x) s = ext_add(s, partial[(size_t)e * nchunks + c]);
+  red[t] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) red[t] = ext_add(red[t], red[t + w]);
+    __syncthreads();
+  }
+  if (t == 0) out[e] = red[0];
+}
+
+// ---- gather / scatter ---------------------------------------------------------------------------------------
+__global__ void k_gather(uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride) {
+  GRID_STRIDE(g, size) dst[g] = src[g * stride + idx];
+}
+// Batched form used by the product driver: every opening of every query in one launch.
+// job j: dst[dst_off[j] + g] = src_j[g * stride_j + idx_j] for g < size_j
+struct GatherJob {
+  const uint32_t* src;
+  uint64_t idx, stride;
+  uint32_t size, dst_off;
+};
+__global__ void k_gather_batched(uint32_t* dst, const GatherJob* jobs) {
+  const GatherJob j = jobs[blockIdx.x];
+  for (uint32_t g = threadIdx.x; g < j.size; g += blockDim.x) dst[j.dst_off + g] = j.src[(size_t)g * j.stride + j.idx];
+}
+// digests: dst[8*j .. 8*j+8) = nodes_j[8*idx_j ..]
+struct DigestJob {
+  const uint32_t* nodes;
+  uint64_t idx;
+};
+__global__ void k_gather_digests(uint32_t* dst, const DigestJob* jobs, size_t njobs) {
+  size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t j = w >> 3;
+  if (j < njobs) dst[w] = jobs[j].nodes[jobs[j].idx * 8 + (w & 7)];
+}
+__global__ void k_scatter(uint32_t* into, const uint32_t* index, size_t cycles, const uint32_t* offsets,
+                          const uint32_t* values) {
+  GRID_STRIDE(cycle, cycles) {
+    for (uint32_t k = index[cycle]; k < index[cycle + 1]; k++) into[offsets[k]] = values[k];
+  }
+}
+__global__ void k_copy_region(uint32_t* into, const uint32_t* from, size_t rows, size_t cols, size_t from_stride,
+                              size_t into_offset, size_t into_stride) {
+  GRID_STRIDE(w, rows * cols) {
+    size_t row = w / cols, col = w % cols;
+    into[into_offset + row * into_stride + col] = from[row * from_stride + col];
+  }
+}
+
+// ---- combos_prepare: tiny, done by one block so that the order of subtraction is irrelevant (exact arithmetic) ----
+__global__ void k_combos_prepare(FpExt* combos, const FpExt* coeff_u, uint32_t combo_count, size_t cycles,
+                                 const uint32_t* reg_sizes, const uint32_t* reg_combo_ids, const uint32_t* reg_pos,
+                                 uint32_t nregs, const FpExt* mix_pows /* nregs + check_size */, uint32_t check_size,
+                                 uint32_t check_pos) {
+  // each (combo, i) cell receives contributions from many registers: one thread per register would race, so
+  // parallelise over destination cells instead: cell = combo * max_size + i
+  const uint32_t max_size = 32;
+  for (uint32_t cell = threadIdx.x; cell < combo_count * max_size; cell += blockDim.x) {
+    const uint32_t combo = cell / max_size, i = cell % max_size;
+    FpExt acc = ext_zero();
+    bool any = false;
+    for (uint32_t r = 0; r < nregs; r++) {
+      if (reg_combo_ids[r] == combo && i < reg_sizes[r]) {
+        acc = ext_add(acc, ext_mul(mix_pows[r], coeff_u[reg_pos[r] + i]));
+        any = true;
+      }
+    }
+    if (any) combos[cycles * combo + i] = ext_sub(combos[cycles * combo + i], acc);
+  }
+  if (threadIdx.x == 0) {
+    FpExt acc = ext_zero();
+    for (uint32_t k = 0; k < check_size; k++) acc = ext_add(acc, ext_mul(mix_pows[nregs + k], coeff_u[check_pos + k]));
+    combos[cycles * combo_count] = ext_sub(combos[cycles * combo_count], acc);
+  }
+}
+
+// ---- combos_divide: in-place synthetic division by (x - z) as a three-kernel chunked Horner scan ---------------
+// q[i] = sum_{j > i} p[j] z^(j-i-1). Chunk c covers [c*L, (c+1)*L). Phase 1: h_c = sum_{j in c} p[j] z^(j - c*L).
+// Phase 2 (one block): carry_c = sum_{c' > c} h_c' z^((c'-c-1) L)  (the value "cur" has when entering chunk c from above).
+// Phase 3: serial Horner inside the chunk seeded with carry_c. Remainder = value after index 0.
+constexpr int DIV_L = 64;  // coefficients per thread
+
+__global__ void k_div_phase1(FpExt* h, const FpExt* p, size_t n, FpExt z) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t nchunks = (n + DIV_L - 1) / DIV_L;
+  if (c >= nchunks) return;
+  size_t lo = c * DIV_L, hi = lo + DIV_L < n ? lo + DIV_L : n;
+  FpExt acc = ext_zero();
+  for (size_t j = hi; j-- > lo;) acc = ext_add(ext_mul(acc, z), p[j]);
+  h[c] = acc;
+}
+// single block; zL = z^DIV_L. carry[c] computed by a serial sweep from the top (nchunks <= 2^18 for n = 2^24;
+// split into 256 threads by a two-level scheme: each thread owns a contiguous run of chunks)
+__global__ void k_div_phase2(FpExt* carry, const FpExt* h, size_t nchunks, FpExt zL) {
+  __shared__ FpExt run_sum[256];   // Horner value of the thread's run (relative to the run start)
+  __shared__ FpExt run_carry[256];
+  const int t = threadIdx.x, T = blockDim.x;
+  const size_t per = (nchunks + T - 1) / T;
+  const size_t lo = (size_t)t * per, hi = lo + per < nchunks ? lo + per : nchunks;
+  FpExt acc = ext_zero();
+  for (size_t c = hi; c-- > lo && hi > lo;) acc = ext_add(ext_mul(acc, zL), h[c]);
+  run_sum[t] = acc;
+  __syncthreads();
+  if (t == 0) {
+    const FpExt zrun = ext_pow(zL, per);
+    FpExt cur = ext_zero();
+    for (int r = T - 1; r >= 0; r--) {
+      run_carry[r] = cur;  // value entering run r from above, at chunk granularity
+      cur = ext_add(ext_mul(cur, zrun), run_sum[r]);
+      // note: a short last run (hi - lo < per) still uses zrun: its missing high chunks are zeros, exact.
+    }
+  }
+  __syncthreads();
+  FpExt cur = run_carry[t];
+  // entering the top chunk of this run: account for chunks missing at the top of a short run
+  if (hi > lo) {
+    size_t missing = per - (hi - lo);
+    if (missing) cur = ext_mul(cur, ext_pow(zL, missing));
+    for (size_t c = hi; c-- > lo;) {
+      carry[c] = cur;
+      cur = ext_add(ext_mul(cur, zL), h[c]);
+    }
+  }
+}
+__global__ void k_div_phase3(FpExt* p, size_t n, const FpExt* carry, FpExt z, FpExt* remainder) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t nchunks = (n + DIV_L - 1) / DIV_L;
+  if (c >= nchunks) return;
+  size_t lo = c * DIV_L, hi = lo + DIV_L < n ? lo + DIV_L : n;
+  FpExt cur = carry[c];
+  for (size_t j = hi; j-- > lo;) {
+    FpExt next = ext_add(ext_mul(z, cur), p[j]);
+    p[j] = cur;
+    cur = next;
+  }
+  if (c == 0) *remainder = cur;
+}
+
+__global__ void k_prefix_products(FpExt* io, size_t n) {  // test-only op in the reference; serial, exact
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    for (size_t i = 1; i < n; i++) io[i] = ext_mul(io[i], io[i - 1]);
+}
+
+__global__ void k_zk_shift(uint32_t* io, size_t total, int bits, const uint32_t* p3_lo, const uint32_t* p3_hi) {
+  GRID_STRIDE(i, total) {
+    uint32_t pos = (uint32_t)(i & ((size_t(1) << bits) - 1));
+    uint32_t e = bits ? (__brev(pos) >> (32 - bits)) : 0u;
+    uint32_t s = fp_mul(p3_hi[e >> 12], p3_lo[e & 4095u]);
+    io[i] = fp_mul(io[i], s);
+  }
+}
+
+}  // namespace r0
+
+using namespace r0;
+
+#define LAUNCH_1D(kernel, n, ...)                                            \
+  do {                                                                       \
+    if ((n) > 0) {                                                           \
+      kernel<<<grid_for(c, (n)), 256, 0, c->stream>>>(__VA_ARGS__);          \
+      count_launch(c);                                                       \
+      R0_CUDA(cudaGetLastError());                                           \
+    }                                                                        \
+  } while (0)
+
+void r0_eltwise_add(Ctx* c, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) { LAUNCH_1D(k_add, n, out, a, b, n); }
+void r0_eltwise_copy(Ctx* c, uint32_t* out, const uint32_t* in, size_t n) {
+  if ((n % 4) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)in % 16) == 0) {
+    LAUNCH_1D(k_copy4, n / 4, (uint4*)out, (const uint4*)in, n / 4);
+  } else {
+    LAUNCH_1D(k_copy, n, out, in, n);
+  }
+}
+void r0_eltwise_zeroize(Ctx* c, uint32_t* io, size_t n) { LAUNCH_1D(k_zeroize, n, io, n); }
+void r0_fill(Ctx* c, uint32_t* io, uint32_t v, size_t n) { LAUNCH_1D(k_fill, n, io, v, n); }
+void r0_eltwise_sum_ext(Ctx* c, uint32_t* out, const uint32_t* in, size_t count, size_t to_add) {
+  LAUNCH_1D(k_sum_ext, count, out, (const uint4*)in, count, to_add);
+}
+void r0_zk_shift(Ctx* c, uint32_t* io, size_t count, int bits) {
+  size_t total = count << bits;
+  LAUNCH_1D(k_zk_shift, total, io, total, bits, c->tab.p3_lo, c->tab.p3_hi);
+}
+
+// small host->device staging helper: stream-ordered scratch that is freed after the kernels that use it
+struct Scratch {
+  Ctx* c;
+  void* d = nullptr;
+  Scratch(Ctx* c_, const void* host, size_t bytes) : c(c_) {
+    R0_CUDA(cudaMallocAsync(&d, bytes ? bytes : 16, c->stream));
+    if (bytes) R0_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  Scratch(Ctx* c_, size_t bytes) : c(c_) { R0_CUDA(cudaMallocAsync(&d, bytes ? bytes : 16, c->stream)); }
+  ~Scratch() { cudaFreeAsync(d, c->stream); }
+  template <typename T>
+  T* as() { return (T*)d; }
+};
+// NOTE: cudaMemcpyAsync from pageable host memory returns after the data has been staged, so the host vectors
+// passed to Scratch may be freed as soon as the constructor returns.
+
+void r0_fri_fold(Ctx* c, uint32_t* out, const uint32_t* in, size_t count, const FpExt& mix) {
+  FpExt pows[16];
+  FpExt cur = ext_one();
+  for (int i = 0; i < 16; i++) {
+    pows[i] = cur;
+    cur = ext_mul(cur, mix);
+  }
+  Scratch mp(c, pows, sizeof(pows));
+  LAUNCH_1D(k_fri_fold, count, out, in, count, mp.as<FpExt>());
+}
+
+#include <algorithm>
+#include <vector>
+
+void r0_mix_poly_coeffs(Ctx* c, uint32_t* out, const FpExt& mix_start, const FpExt& mix, const uint32_t* in,
+                        const uint32_t* combos_host, size_t input_size, size_t count) {
+  if (input_size == 0 || count == 0) return;
+  std::vector<FpExt> pows(input_size);
+  FpExt cur = mix_start;
+  for (size_t i = 0; i < input_size; i++) {
+    pows[i] = cur;
+    cur = ext_mul(cur, mix);
+  }
+  std::vector<uint32_t> order(input_size);
+  for (size_t i = 0; i < input_size; i++) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return combos_host[a] < combos_host[b]; });
+  std::vector<uint32_t> seg_begin, seg_combo;
+  for (size_t q = 0; q < input_size; q++) {
+    if (q == 0 || combos_host[order[q]] != combos_host[order[q - 1]]) {
+      seg_begin.push_back((uint32_t)q);
+      seg_combo.push_back(combos_host[order[q]]);
+    }
+  }
+  seg_begin.push_back((uint32_t)input_size);
+  Scratch d_pows(c, pows.data(), pows.size() * sizeof(FpExt));
+  Scratch d_order(c, order.data(), order.size() * 4);
+  Scratch d_sb(c, seg_begin.data(), seg_begin.size() * 4);
+  Scratch d_sc(c, seg_combo.data(), seg_combo.size() * 4);
+  LAUNCH_1D(k_mix_poly_coeffs, count, (uint4*)out, in, count, d_order.as<uint32_t>(), d_sb.as<uint32_t>(),
+            d_sc.as<uint32_t>(), (uint32_t)seg_combo.size(), d_pows.as<FpExt>());
+}
+
+void r0_batch_evaluate_any(Ctx* c, const uint32_t* coeffs, size_t n, const uint32_t* which_dev, const uint32_t* xs_dev,
+                           uint32_t* out_dev, size_t eval_count) {
+  if (eval_count == 0) return;
+  const size_t per_block = (size_t)EV_T * EV_CH;
+  const int nchunks = (int)((n + per_block - 1) / per_block);
+  Scratch xt(c, eval_count * EV_T * sizeof(FpExt));
+  Scratch xq(c, eval_count * EV_CH * sizeof(FpExt));
+  Scratch xc(c, eval_count * nchunks * sizeof(FpExt));
+  Scratch partial(c, eval_count * nchunks * sizeof(FpExt));
+  for (size_t e0 = 0; e0 < eval_count; e0 += 65535) {
+    size_t ne = eval_count - e0 < 65535 ? eval_count - e0 : 65535;
+    k_eval_tables<<<(unsigned)ne, EV_T, 0, c->stream>>>(xt.as<FpExt>() + e0 * EV_T, xq.as<FpExt>() + e0 * EV_CH,
+                                                        xc.as<FpExt>() + e0 * nchunks, (const FpExt*)xs_dev + e0, nchunks);
+    k_eval_partial<<<dim3(nchunks, (unsigned)ne), EV_T, 0, c->stream>>>(
+        partial.as<FpExt>() + e0 * nchunks, coeffs, n, which_dev + e0, xt.as<FpExt>() + e0 * EV_T,
+        xq.as<FpExt>() + e0 * EV_CH, xc.as<FpExt>() + e0 * nchunks, nchunks);
+    k_eval_final<<<(unsigned)ne, 256, 0, c->stream>>>((FpExt*)out_dev + e0, partial.as<FpExt>() + e0 * nchunks, nchunks);
+    count_launch(c, 3);
+  }
+  R0_CUDA(cudaGetLastError());
+}
+
+void r0_gather_sample(Ctx* c, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride) {
+  LAUNCH_1D(k_gather, size, dst, src, idx, size, stride);
+}
+void r0_scatter(Ctx* c, uint32_t* into, const uint32_t* index_host, size_t index_len, const uint32_t* offsets_host,
+                const uint32_t* values_host) {
+  if (index_len < 2) return;
+  size_t nvals = index_host[index_len - 1];
+  Scratch d_index(c, index_host, index_len * 4);
+  Scratch d_off(c, offsets_host, nvals * 4);
+  Scratch d_val(c, values_host, nvals * 4);
+  LAUNCH_1D(k_scatter, index_len - 1, into, d_index.as<uint32_t>(), index_len - 1, d_off.as<uint32_t>(),
+            d_val.as<uint32_t>());
+}
+void r0_copy_elem_slice(Ctx* c, uint32_t* into, const uint32_t* from_host, size_t from_rows, size_t from_cols,
+                        size_t from_offset, size_t from_stride, size_t into_offset, size_t into_stride) {
+  if (from_rows == 0 || from_cols == 0) return;
+  size_t span = (from_rows - 1) * from_stride + from_cols;
+  Scratch d_from(c, from_host + from_offset, span * 4);
+  LAUNCH_1D(k_copy_region, from_rows * from_cols, into, d_from.as<uint32_t>(), from_rows, from_cols, from_stride,
+            into_offset, into_stride);
+}
+void r0_prefix_products(Ctx* c, uint32_t* io, size_t n) {
+  k_prefix_products<<<1, 32, 0, c->stream>>>((FpExt*)io, n);
+  count_launch(c);
+  R0_CUDA(cudaGetLastError());
+}
+
+void r0_combos_prepare(Ctx* c, uint32_t* combos, const FpExt* coeff_u_host, size_t coeff_u_len, uint32_t combo_count,
+                       size_t cycles, const uint32_t* reg_sizes, const uint32_t* reg_combo_ids, uint32_t nregs,
+                       const FpExt& mix, uint32_t check_size) {
+  std::vector<FpExt> pows(nregs + check_size);
+  std::vector<uint32_t> pos(nregs);
+  FpExt cur = ext_one();
+  uint32_t cur_pos = 0;
+  for (uint32_t r = 0; r < nregs; r++) {
+    R0_CHECK(reg_sizes[r] <= 32, "combos_prepare: register with more than 32 taps");
+    pows[r] = cur;
+    pos[r] = cur_pos;
+    cur = ext_mul(cur, mix);
+    cur_pos += reg_sizes[r];
+  }
+  for (uint32_t k = 0; k < check_size; k++) {
+    pows[nregs + k] = cur;
+    cur = ext_mul(cur, mix);
+  }
+  R0_CHECK(cur_pos + check_size <= coeff_u_len, "combos_prepare: coeff_u too short");
+  Scratch d_u(c, coeff_u_host, coeff_u_len * sizeof(FpExt));
+  Scratch d_sz(c, reg_sizes, nregs * 4);
+  Scratch d_id(c, reg_combo_ids, nregs * 4);
+  Scratch d_pos(c, pos.data(), nregs * 4);
+  Scratch d_pw(c, pows.data(), pows.size() * sizeof(FpExt));
+  k_combos_prepare<<<1, 256, 0, c->stream>>>((FpExt*)combos, d_u.as<FpExt>(), combo_count, cycles, d_sz.as<uint32_t>(),
+                                             d_id.as<uint32_t>(), d_pos.as<uint32_t>(), nregs, d_pw.as<FpExt>(),
+                                             check_size, cur_pos);
+  count_launch(c);
+  R0_CUDA(cudaGetLastError());
+}
+
+// poly: n FpExt coefficients, divided in place by (x - z); the remainder is written to *remainder_dev.
+void r0_poly_divide(Ctx* c, uint32_t* poly, size_t n, const FpExt& z, uint32_t* remainder_dev) {
+  if (n == 0) return;
+  size_t nchunks = (n + DIV_L - 1) / DIV_L;
+  Scratch h(c, nchunks * sizeof(FpExt));
+  Scratch carry(c, nchunks * sizeof(FpExt));
+  FpExt zL = ext_pow(z, DIV_L);
+  unsigned blocks = (unsigned)((nchunks + 127) / 128);
+  k_div_phase1<<<blocks, 128, 0, c->stream>>>(h.as<FpExt>(), (const FpExt*)poly, n, z);
+  k_div_phase2<<<1, 256, 0, c->stream>>>(carry.as<FpExt>(), h.as<FpExt>(), nchunks, zL);
+  k_div_phase3<<<blocks, 128, 0, c->stream>>>((FpExt*)poly, n, carry.as<FpExt>(), z, (FpExt*)remainder_dev);
+  count_launch(c, 3);
+  R0_CUDA(cudaGetLastError());
+}
+
+// ---- batched query openings (product driver) ------------------------------------------------------------------
+void r0_gather_batched(Ctx* c, uint32_t* dst, const void* jobs_host, size_t njobs) {
+  if (njobs == 0) return;
+  Scratch d_jobs(c, jobs_host, njobs * sizeof(GatherJob));
+  k_gather_batched<<<(unsigned)njobs, 128, 0, c->stream>>>(dst, d_jobs.as<GatherJob>());
+  count_launch(c);
+  R0_CUDA(cudaGetLastError());
+}
+void r0_gather_digests(Ctx* c, uint32_t* dst, const void* jobs_host, size_t njobs) {
+  if (njobs == 0) return;
+  Scratch d_jobs(c, jobs_host, njobs * sizeof(DigestJob));
+  k_gather_digests<<<(unsigned)((njobs * 8 + 255) / 256), 256, 0, c->stream>>>(dst, d_jobs.as<DigestJob>(), njobs);
+  count_launch(c);
+  R0_CUDA(cudaGetLastError());
+}

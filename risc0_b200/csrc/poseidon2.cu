@@ -1,0 +1,225 @@
+// Poseidon2 (BabyBear, t = 24, rate 16, capacity 8, x^7, 4 + 21 + 4 rounds) row hashing and Merkle folding, sm_100a.
+//
+// Replaces: Hal::hash_rows (risc0/zkp/src/hal/cpu.rs:555-567 -> poseidon2/mod.rs:221-244 unpadded_hash) and
+//           Hal::hash_fold (cpu.rs:569-581 -> poseidon2/mod.rs:46-58 hash_pair); reference GPU kernels
+//           risc0/sys/kernels/zkp/cuda/supra/poseidon2.cuh:112-163 (one launch + device sync per tree level).
+//
+// The whole 24-word state of a permutation lives in registers (one row / one node per thread). The kernels are
+// INT32-pipe bound (1356 Montgomery products per permutation): HBM traffic is 4*cols + 32 bytes per row for
+// hash_rows and 96 bytes per node for the fold, far under the memory roofline.
+//  * hash_rows reads the column-major matrix with one coalesced 128 B line per warp per column.
+//  * merkle_fold_tree folds up to 9 tree levels per launch: a block owns a 512-leaf subtree, keeps the shrinking
+//    levels in shared memory and writes every level to the heap array, so a 2^22-leaf tree takes 3 launches
+//    instead of 22 launch+sync pairs.
+#include "ctx.h"
+#include "tables/poseidon2_tables.h"
+
+namespace r0 {
+
+__constant__ uint32_t c_rc_full[8 * 24];
+__constant__ uint32_t c_rc_partial[21];
+__constant__ uint32_t c_diag[24];
+
+__device__ __forceinline__ uint32_t sbox7(uint32_t x) {
+  uint32_t x2 = fp_mul(x, x);
+  uint32_t x4 = fp_mul(x2, x2);
+  uint32_t x6 = fp_mul(x4, x2);
+  return fp_mul(x6, x);
+}
+__device__ __forceinline__ uint32_t dbl(uint32_t x) { return fp_add(x, x); }
+
+// M_ext = circ(2*M4, M4, ..., M4) with M4 the 4x4 matrix of poseidon2/mod.rs:139-151
+__device__ __forceinline__ void m_ext(uint32_t (&c)[24]) {
+  uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    uint32_t x0 = c[4 * i], x1 = c[4 * i + 1], x2 = c[4 * i + 2], x3 = c[4 * i + 3];
+    uint32_t t0 = fp_add(x0, x1);
+    uint32_t t1 = fp_add(x2, x3);
+    uint32_t t2 = fp_add(dbl(x1), t1);
+    uint32_t t3 = fp_add(dbl(x3), t0);
+    uint32_t t4 = fp_add(dbl(dbl(t1)), t3);
+    uint32_t t5 = fp_add(dbl(dbl(t0)), t2);
+    uint32_t t6 = fp_add(t3, t5);
+    uint32_t t7 = fp_add(t2, t4);
+    c[4 * i] = t6;
+    c[4 * i + 1] = t5;
+    c[4 * i + 2] = t7;
+    c[4 * i + 3] = t4;
+    s0 = fp_add(s0, t6);
+    s1 = fp_add(s1, t5);
+    s2 = fp_add(s2, t7);
+    s3 = fp_add(s3, t4);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    c[4 * i] = fp_add(c[4 * i], s0);
+    c[4 * i + 1] = fp_add(c[4 * i + 1], s1);
+    c[4 * i + 2] = fp_add(c[4 * i + 2], s2);
+    c[4 * i + 3] = fp_add(c[4 * i + 3], s3);
+  }
+}
+
+__device__ __forceinline__ void full_round(uint32_t (&c)[24], int r) {
+#pragma unroll
+  for (int i = 0; i < 24; i++) c[i] = sbox7(fp_add(c[i], c_rc_full[r * 24 + i]));
+  m_ext(c);
+}
+
+__device__ __forceinline__ void partial_round(uint32_t (&c)[24], int r) {
+  c[0] = sbox7(fp_add(c[0], c_rc_partial[r]));
+  // sum of 24 canonical values: pairwise tree keeps the dependency chain short
+  uint32_t p[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) p[i] = fp_add(c[2 * i], c[2 * i + 1]);
+#pragma unroll
+  for (int i = 0; i < 6; i++) p[i] = fp_add(p[2 * i], p[2 * i + 1]);
+  uint32_t sum = fp_add(fp_add(fp_add(p[0], p[1]), fp_add(p[2], p[3])), fp_add(p[4], p[5]));
+#pragma unroll
+  for (int i = 0; i < 24; i++) c[i] = fp_add(sum, fp_mul(c_diag[i], c[i]));
+}
+
+__device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) {
+  m_ext(c);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) full_round(c, r);
+#pragma unroll 1
+  for (int r = 0; r < 21; r++) partial_round(c, r);
+#pragma unroll 1
+  for (int r = 4; r < 8; r++) full_round(c, r);
+}
+
+// out[row] = sponge over matrix[j*rows + row], j < cols (overwrite mode, zero-filled tail, empty input = one permute)
+__global__ void __launch_bounds__(256) p2_hash_rows_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix,
+                                                         size_t rows, uint32_t cols) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  uint32_t c[24];
+#pragma unroll
+  for (int i = 0; i < 24; i++) c[i] = 0;
+  // single permutation call site (keeps the unrolled round code in the binary once); tail block is zero-filled
+  uint32_t done = 0;
+  do {
+    if (done + 16 <= cols) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) c[i] = matrix[(size_t)(done + i) * rows + row];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) c[i] = (done + i < cols) ? matrix[(size_t)(done + i) * rows + row] : 0u;
+    }
+    p2_permute(c);
+    done += 16;
+  } while (done < cols);
+  uint4* o = reinterpret_cast<uint4*>(out + row * 8);
+  o[0] = make_uint4(c[0], c[1], c[2], c[3]);
+  o[1] = make_uint4(c[4], c[5], c[6], c[7]);
+}
+
+__device__ __forceinline__ void load_pair(uint32_t (&c)[24], const uint32_t* __restrict__ in) {
+  const uint4* p = reinterpret_cast<const uint4*>(in);
+  uint4 a = p[0], b = p[1], d = p[2], e = p[3];
+  c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w;
+  c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+  c[8] = d.x; c[9] = d.y; c[10] = d.z; c[11] = d.w;
+  c[12] = e.x; c[13] = e.y; c[14] = e.z; c[15] = e.w;
+#pragma unroll
+  for (int i = 16; i < 24; i++) c[i] = 0;
+}
+
+// one level: io[out_size + i] = H(io[in_size + 2i] || io[in_size + 2i + 1])
+__global__ void __launch_bounds__(256) p2_hash_fold_kernel(uint32_t* io, size_t in_size, size_t out_size) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_size) return;
+  uint32_t c[24];
+  load_pair(c, io + (in_size + 2 * i) * 8);
+  p2_permute(c);
+  uint4* o = reinterpret_cast<uint4*>(io + (out_size + i) * 8);
+  o[0] = make_uint4(c[0], c[1], c[2], c[3]);
+  o[1] = make_uint4(c[4], c[5], c[6], c[7]);
+}
+
+// Several levels per launch. A block takes 2*B consecutive nodes of the level of `in_size` nodes (B = blockDim.x),
+// and produces `levels` levels (B, B/2, ... nodes), each written to its heap position nodes[size + index].
+__global__ void __launch_bounds__(256) p2_fold_tree_kernel(uint32_t* nodes, size_t in_size, int levels) {
+  __shared__ uint32_t sh[256 * 8];
+  const int B = blockDim.x;
+  const int t = threadIdx.x;
+  uint32_t c[24];
+  size_t out_size = in_size >> 1;
+  size_t base = (size_t)blockIdx.x * B;  // first output node of this block at the current level
+  int active = B;
+  for (int lv = 0; lv < levels; lv++) {
+    if (lv > 0) {
+      __syncthreads();  // previous readers of sh are done
+      if (t < active) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) sh[t * 8 + i] = c[i];
+      }
+      __syncthreads();
+      active >>= 1;
+      out_size >>= 1;
+      base >>= 1;
+      if (active == 0 || out_size == 0) break;  // uniform across the block
+    }
+    if (t < active && base + t < out_size) {
+      if (lv == 0) {
+        load_pair(c, nodes + (in_size + 2 * (base + t)) * 8);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) c[i] = sh[2 * t * 8 + i];
+#pragma unroll
+        for (int i = 16; i < 24; i++) c[i] = 0;
+      }
+      p2_permute(c);
+      uint4* o = reinterpret_cast<uint4*>(nodes + (out_size + base + t) * 8);
+      o[0] = make_uint4(c[0], c[1], c[2], c[3]);
+      o[1] = make_uint4(c[4], c[5], c[6], c[7]);
+    }
+  }
+}
+
+}  // namespace r0
+
+using namespace r0;
+
+void r0_poseidon2_init(Ctx* c) {
+  R0_CUDA(cudaMemcpyToSymbolAsync(c_rc_full, R0_P2_RC_FULL_MONT, sizeof(R0_P2_RC_FULL_MONT), 0, cudaMemcpyHostToDevice,
+                                  c->stream));
+  R0_CUDA(cudaMemcpyToSymbolAsync(c_rc_partial, R0_P2_RC_PARTIAL_MONT, sizeof(R0_P2_RC_PARTIAL_MONT), 0,
+                                  cudaMemcpyHostToDevice, c->stream));
+  R0_CUDA(cudaMemcpyToSymbolAsync(c_diag, R0_P2_DIAG_MONT, sizeof(R0_P2_DIAG_MONT), 0, cudaMemcpyHostToDevice,
+                                  c->stream));
+  R0_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
+  if (rows == 0) return;
+  R0_CHECK(cols <= 0xffffffffull, "hash_rows: too many columns");
+  p2_hash_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols);
+  count_launch(c);
+  R0_CUDA(cudaGetLastError());
+}
+
+void r0_p2_hash_fold(Ctx* c, uint32_t* io, size_t in_size, size_t out_size) {
+  R0_CHECK(in_size == 2 * out_size, "hash_fold: input_size must be 2 * output_size");
+  if (out_size == 0) return;
+  p2_hash_fold_kernel<<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(io, in_size, out_size);
+  count_launch(c);
+  R0_CUDA(cudaGetLastError());
+}
+
+// All levels below `leaves` (a power of two): nodes[leaves .. 2*leaves) are the leaf digests, fills nodes[1 .. leaves).
+void r0_p2_merkle_fold_all(Ctx* c, uint32_t* nodes, size_t leaves) {
+  size_t in_size = leaves;
+  while (in_size > 1) {
+    size_t out_size = in_size / 2;
+    int B = out_size >= 256 ? 256 : (int)out_size;
+    int levels = 1;
+    while ((1 << levels) <= B) levels++;  // B = 2^j -> j + 1 levels (B, B/2, ..., 1)
+    unsigned blocks = (unsigned)((out_size + B - 1) / B);
+    p2_fold_tree_kernel<<<blocks, B, 0, c->stream>>>(nodes, in_size, levels);
+    count_launch(c);
+    in_size >>= levels;
+  }
+  R0_CUDA(cudaGetLastError());
+}

@@ -1,0 +1,294 @@
+"""Host-side mirror of the reference `Hal` / `Buffer` traits (risc0/zkp/src/hal/mod.rs:39-258) over the r0b200 C ABI.
+
+Method names, argument order and meaning follow the Rust trait so the parity tests read like the reference's own
+`hal::testutil` A/B tests (hal/mod.rs:319-616). Host data are numpy uint32 arrays of Montgomery words
+(Elem = 1 word, ExtElem = 4 words, Digest = 8 words).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import R0B200Error, check, load_library
+
+_u32p = C.POINTER(C.c_uint32)
+POSEIDON2, SHA256 = 0, 1
+P = 15 * 2**27 + 1
+INVALID = 0xFFFFFFFF
+CHECK_SIZE = 16
+
+
+def _np_ptr(a):
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_u32p)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+class _Alloc:
+    """owns one device allocation; freed (stream-ordered) when the last Buffer view drops"""
+
+    def __init__(self, hal, nbytes):
+        self.hal = hal
+        self.nbytes = nbytes
+        p = C.c_void_p()
+        check(hal._l.r0b200_alloc(hal._ctx, C.c_size_t(nbytes), C.byref(p)))
+        self.ptr = p.value
+
+    def __del__(self):
+        try:
+            if self.ptr and self.hal._ctx:
+                self.hal._l.r0b200_free(self.hal._ctx, C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+class Buffer:
+    """trait Buffer<T> (hal/mod.rs:39-53): aliasing slices, get_at, view, to_vec. `words` = u32 words per element."""
+
+    def __init__(self, hal, name, size, words, alloc=None, offset=0):
+        self.hal, self._name, self._size, self.words, self.offset = hal, name, int(size), words, int(offset)
+        self.alloc = alloc if alloc is not None else _Alloc(hal, self._size * words * 4)
+
+    def name(self):
+        return self._name
+
+    def size(self):
+        return self._size
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.alloc.ptr + self.offset * self.words * 4)
+
+    def slice(self, offset, size):
+        assert offset + size <= self._size
+        return Buffer(self.hal, self._name, size, self.words, self.alloc, self.offset + offset)
+
+    def view(self):
+        out = np.empty(self._size * self.words, dtype=np.uint32)
+        check(self.hal._l.r0b200_copy_d2h(self.hal._ctx, _np_ptr(out), self.ptr, C.c_size_t(out.nbytes)))
+        return out
+
+    to_vec = view
+
+    def get_at(self, idx):
+        out = np.empty(self.words, dtype=np.uint32)
+        src = C.c_void_p(self.alloc.ptr + (self.offset + idx) * self.words * 4)
+        check(self.hal._l.r0b200_copy_d2h(self.hal._ctx, _np_ptr(out), src, C.c_size_t(out.nbytes)))
+        return out
+
+    def write(self, data):
+        data = _u32(data)
+        assert data.size == self._size * self.words, (data.size, self._size, self.words)
+        check(self.hal._l.r0b200_copy_h2d(self.hal._ctx, self.ptr, _np_ptr(data), C.c_size_t(data.nbytes)))
+        # the copy is stream-ordered from pageable memory: staged before the call returns
+
+
+def _lg(n):
+    lg = int(n).bit_length() - 1
+    if n <= 0 or (1 << lg) != n:
+        raise R0B200Error("size %d is not a power of two" % n)
+    return lg
+
+
+class B200Hal:
+    """impl Hal for the B200 backend. One instance = one device ordinal + one stream (hal/cuda.rs:397-421 analogue)."""
+
+    def __init__(self, device=0, hashfn="poseidon2"):
+        self._l = load_library()
+        self._ctx = C.c_void_p()
+        self.hash = {"poseidon2": POSEIDON2, "sha-256": SHA256}[hashfn]
+        self.hashfn = hashfn
+        check(self._l.r0b200_create(int(device), C.byref(self._ctx)))
+
+    def close(self):
+        if self._ctx:
+            self._l.r0b200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- introspection
+    def has_unified_memory(self):
+        return False
+
+    def sync(self):
+        check(self._l.r0b200_sync(self._ctx))
+
+    def launch_count(self):
+        return int(self._l.r0b200_launch_count(self._ctx))
+
+    def stream(self):
+        return self._l.r0b200_stream(self._ctx)
+
+    def timer_start(self):
+        check(self._l.r0b200_timer_start(self._ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self._l.r0b200_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    # ---- allocation (hal/mod.rs:67-100)
+    def alloc_elem(self, name, size):
+        return Buffer(self, name, size, 1)
+
+    def alloc_extelem(self, name, size):
+        return Buffer(self, name, size, 4)
+
+    def alloc_digest(self, name, size):
+        return Buffer(self, name, size, 8)
+
+    def alloc_u32(self, name, size):
+        return Buffer(self, name, size, 1)
+
+    def alloc_elem_init(self, name, size, value_mont):
+        b = self.alloc_elem(name, size)
+        check(self._l.r0b200_fill_u32(self._ctx, b.ptr, C.c_uint32(int(value_mont)), C.c_size_t(size)))
+        return b
+
+    def alloc_extelem_zeroed(self, name, size):
+        b = self.alloc_extelem(name, size)
+        check(self._l.r0b200_fill_u32(self._ctx, b.ptr, C.c_uint32(0), C.c_size_t(size * 4)))
+        return b
+
+    def _copy_from(self, name, data, words):
+        data = _u32(data)
+        b = Buffer(self, name, data.size // words, words)
+        b.write(data)
+        return b
+
+    def copy_from_elem(self, name, data):
+        return self._copy_from(name, data, 1)
+
+    def copy_from_extelem(self, name, data):
+        return self._copy_from(name, data, 4)
+
+    def copy_from_digest(self, name, data):
+        return self._copy_from(name, data, 8)
+
+    def copy_from_u32(self, name, data):
+        return self._copy_from(name, data, 1)
+
+    # ---- NTT family
+    def batch_expand_into_evaluate_ntt(self, output, input, count, expand_bits):
+        in_row, out_row = input.size() // count, output.size() // count
+        if in_row * count != input.size() or out_row != in_row << expand_bits:
+            raise R0B200Error("batch_expand_into_evaluate_ntt: size mismatch")
+        check(self._l.r0b200_batch_expand_into_evaluate_ntt(self._ctx, output.ptr, input.ptr, C.c_size_t(count),
+                                                            C.c_uint32(_lg(in_row)), C.c_uint32(expand_bits)))
+
+    def batch_interpolate_ntt(self, io, count):
+        row = io.size() // count
+        assert row * count == io.size()
+        check(self._l.r0b200_batch_interpolate_ntt(self._ctx, io.ptr, C.c_size_t(count), C.c_uint32(_lg(row))))
+
+    def batch_interpolate_ntt_zk(self, io, count):
+        """fused batch_interpolate_ntt + zk_shift (make_coeffs, prove/prover.rs:38-48)"""
+        row = io.size() // count
+        check(self._l.r0b200_batch_interpolate_ntt_zk(self._ctx, io.ptr, C.c_size_t(count), C.c_uint32(_lg(row))))
+
+    def batch_bit_reverse(self, io, count):
+        row = io.size() // count
+        assert row * count == io.size()
+        check(self._l.r0b200_batch_bit_reverse(self._ctx, io.ptr, C.c_size_t(count), C.c_uint32(_lg(row))))
+
+    def zk_shift(self, io, count):
+        row = io.size() // count
+        check(self._l.r0b200_zk_shift(self._ctx, io.ptr, C.c_size_t(count), C.c_uint32(_lg(row))))
+
+    def batch_evaluate_any(self, coeffs, poly_count, which, xs, out):
+        n = coeffs.size() // poly_count
+        assert n * poly_count == coeffs.size() and xs.size() == which.size() == out.size()
+        check(self._l.r0b200_batch_evaluate_any(self._ctx, coeffs.ptr, C.c_size_t(poly_count), C.c_uint32(_lg(n)),
+                                                which.ptr, xs.ptr, out.ptr, C.c_size_t(which.size())))
+
+    def mix_poly_coeffs(self, out, mix_start, mix, input, combos, input_size, count):
+        """`combos` is the host u32 array of combo ids (the reference uploads it with copy_from_u32 first)"""
+        combos = _u32(combos)
+        assert combos.size == input_size and input.size() == input_size * count
+        check(self._l.r0b200_mix_poly_coeffs(self._ctx, out.ptr, _np_ptr(_u32(mix_start)), _np_ptr(_u32(mix)),
+                                             input.ptr, _np_ptr(combos), C.c_size_t(input_size), C.c_size_t(count)))
+
+    # ---- element-wise
+    def eltwise_add_elem(self, output, input1, input2):
+        assert output.size() == input1.size() == input2.size()
+        check(self._l.r0b200_eltwise_add_elem(self._ctx, output.ptr, input1.ptr, input2.ptr, C.c_size_t(output.size())))
+
+    def eltwise_sum_extelem(self, output, input):
+        count = output.size() // 4
+        to_add = input.size() // count
+        assert output.size() == 4 * count and input.size() == count * to_add
+        check(self._l.r0b200_eltwise_sum_extelem(self._ctx, output.ptr, input.ptr, C.c_size_t(count), C.c_size_t(to_add)))
+
+    def eltwise_copy_elem(self, output, input):
+        assert output.size() == input.size()
+        check(self._l.r0b200_eltwise_copy_elem(self._ctx, output.ptr, input.ptr, C.c_size_t(output.size())))
+
+    def eltwise_copy_elem_slice(self, into, from_host, from_rows, from_cols, from_offset, from_stride, into_offset,
+                                into_stride):
+        check(self._l.r0b200_eltwise_copy_elem_slice(self._ctx, into.ptr, _np_ptr(_u32(from_host)),
+                                                     C.c_size_t(from_rows), C.c_size_t(from_cols),
+                                                     C.c_size_t(from_offset), C.c_size_t(from_stride),
+                                                     C.c_size_t(into_offset), C.c_size_t(into_stride)))
+
+    def eltwise_zeroize_elem(self, elems):
+        check(self._l.r0b200_eltwise_zeroize_elem(self._ctx, elems.ptr, C.c_size_t(elems.size())))
+
+    def fri_fold(self, output, input, mix):
+        count = output.size() // 4
+        assert input.size() == output.size() * 16
+        check(self._l.r0b200_fri_fold(self._ctx, output.ptr, input.ptr, C.c_size_t(count), _np_ptr(_u32(mix))))
+
+    # ---- hashing
+    def hash_rows(self, output, matrix):
+        rows = output.size()
+        cols = matrix.size() // rows if rows else 0
+        assert matrix.size() == rows * cols
+        check(self._l.r0b200_hash_rows(self._ctx, self.hash, output.ptr, matrix.ptr, C.c_size_t(rows), C.c_size_t(cols)))
+
+    def hash_fold(self, io, input_size, output_size):
+        assert io.size() >= 2 * input_size
+        check(self._l.r0b200_hash_fold(self._ctx, self.hash, io.ptr, C.c_size_t(input_size), C.c_size_t(output_size)))
+
+    def merkle_build(self, nodes, matrix, rows, cols):
+        """MerkleTreeProver::new's hash_rows + all hash_fold levels in one call"""
+        assert nodes.size() == 2 * rows and matrix.size() == rows * cols
+        check(self._l.r0b200_merkle_build(self._ctx, self.hash, nodes.ptr, matrix.ptr, C.c_size_t(rows), C.c_size_t(cols)))
+
+    # ---- gather / scatter / misc
+    def gather_sample(self, dst, src, idx, size, stride):
+        check(self._l.r0b200_gather_sample(self._ctx, dst.ptr, src.ptr, C.c_size_t(idx), C.c_size_t(size),
+                                           C.c_size_t(stride)))
+
+    def scatter(self, into, index, offsets, values):
+        index, offsets, values = _u32(index), _u32(offsets), _u32(values)
+        if index.size == 0:
+            return
+        check(self._l.r0b200_scatter(self._ctx, into.ptr, _np_ptr(index), C.c_size_t(index.size), _np_ptr(offsets),
+                                     _np_ptr(values)))
+
+    def prefix_products(self, io):
+        check(self._l.r0b200_prefix_products(self._ctx, io.ptr, C.c_size_t(io.size())))
+
+    def combos_prepare(self, combos, coeff_u, combo_count, cycles, reg_sizes, reg_combo_ids, mix):
+        coeff_u, reg_sizes, reg_combo_ids = _u32(coeff_u), _u32(reg_sizes), _u32(reg_combo_ids)
+        check(self._l.r0b200_combos_prepare(self._ctx, combos.ptr, _np_ptr(coeff_u), C.c_size_t(coeff_u.size // 4),
+                                            C.c_uint32(combo_count), C.c_size_t(cycles), _np_ptr(reg_sizes),
+                                            _np_ptr(reg_combo_ids), C.c_uint32(reg_sizes.size), _np_ptr(_u32(mix))))
+
+    def combos_divide(self, combos, chunks, cycles):
+        """chunks: list of (i, [pow ext elems]) as in hal/mod.rs:236-257; chunk order = position in `combos`"""
+        pow_begin, pows = [0], []
+        for _, ps in chunks:
+            for p in ps:
+                pows.extend(int(x) for x in p)
+            pow_begin.append(len(pows) // 4)
+        pows = _u32(pows if pows else [0, 0, 0, 0])
+        check(self._l.r0b200_combos_divide(self._ctx, combos.ptr, C.c_size_t(len(chunks)), _np_ptr(_u32(pow_begin)),
+                                           _np_ptr(pows), C.c_size_t(cycles)))
