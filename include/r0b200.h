@@ -117,6 +117,28 @@ r0b200_err r0b200_combos_prepare(r0b200_ctx* ctx, uint32_t* combos, const uint32
 r0b200_err r0b200_combos_divide(r0b200_ctx* ctx, uint32_t* combos, size_t nchunks, const uint32_t* pow_begin_host,
                                 const uint32_t* pows_host, size_t cycles);
 
+/* ---- circuit (CircuitHal) ---- */
+/* CircuitHal::eval_check for the rv32im circuit (hal/mod.rs:279-289; risc0_circuit_rv32im_cuda_eval_check,
+ * rv32im-sys/src/lib.rs:87-133; CPU spec rv32im/src/prove/hal/cpu.rs:145-208). check: 4 x (4 << po2) words out;
+ * groups are the evaluated matrices (cols x (4 << po2)): ctrl = code group (1 col, unused by the constraints, kept for
+ * signature parity), data (211), accum (103); mix (36 words) and out = globals (90 words) are device buffers;
+ * poly_mix_host = 4 words. The poly-mix power table and the root of unity are derived inside. */
+r0b200_err r0b200_eval_check_rv32im(r0b200_ctx* ctx, uint32_t* check, const uint32_t* ctrl, const uint32_t* data,
+                                    const uint32_t* accum, const uint32_t* mix, const uint32_t* out,
+                                    const uint32_t* poly_mix_host, uint32_t po2);
+
+/* ---- whole segment (the Hal's caller on the hot path) ---- */
+/* prove_core's prove_inner block for a committed rv32im witness (rv32im/src/prove/hal/mod.rs:171-222 ->
+ * zkp/src/prove/prover.rs:81-393 -> prove/fri.rs:77-126): commits code (1 x N), data (211 x N), accum (103 x N),
+ * N = 2^po2, runs eval_check, DEEP and FRI, and writes the seal (u32 words, the reference's seal format) to host
+ * memory. code/data/accum are column-major witness matrices, device pointers unless witness_on_host != 0 (then they
+ * are copied with stream-ordered H2D copies first - pinned memory makes those asynchronous). global_host: 90 words.
+ * Optional outputs (may be NULL): every committed Merkle root in commit order, and the 50 drawn query positions. */
+r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* code, const uint32_t* data,
+                               const uint32_t* accum, int witness_on_host, const uint32_t* global_host,
+                               uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
+                               size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host);
+
 #ifdef __cplusplus
 }
 #endif

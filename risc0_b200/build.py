@@ -34,6 +34,36 @@ def headers():
             glob.glob(os.path.join(CSRC, "gen", "*.cuh")) + [os.path.join(HERE, "..", "include", "r0b200.h")])
 
 
+def ptx_sources():
+    return sorted(glob.glob(os.path.join(CSRC, "gen", "*.ptx")))
+
+
+def generate(force=False):
+    """(re)create csrc/gen/* from the committed circuit IR when missing or stale (tools/gen_eval_check.py)"""
+    root = os.path.join(HERE, "..")
+    gen = os.path.join(root, "tools", "gen_eval_check.py")
+    for name in ("rv32im",):
+        irf = os.path.join(HERE, "circuits", name + ".ir.json.gz")
+        launcher = os.path.join(CSRC, "gen", "eval_check_%s.cu" % name)
+        ptx = glob.glob(os.path.join(CSRC, "gen", "eval_check_%s_p*.ptx" % name))
+        newest_in = max(os.path.getmtime(gen), os.path.getmtime(irf),
+                        os.path.getmtime(os.path.join(root, "tools", "circuit_ir.py")))
+        if force or not ptx or not os.path.exists(launcher) or min(os.path.getmtime(f) for f in ptx) < newest_in:
+            r = subprocess.run([sys.executable, gen, name, "--from-ir"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("generator failed:\n%s\n%s" % (r.stdout, r.stderr))
+
+
+def _assemble(ptx, cubin, verbose):
+    cmd = [os.path.join(os.path.dirname(NVCC), "ptxas"), "-arch=sm_100a", "-O3", ptx, "-o", cubin]
+    if verbose:
+        cmd.append("-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("ptxas failed for %s:\n%s\n%s" % (ptx, r.stdout, r.stderr))
+    return ptx, r.stderr
+
+
 def _compile(src, obj, verbose):
     cmd = [NVCC] + FLAGS + ["-I", CSRC, "-c", src, "-o", obj]
     if verbose:
@@ -47,6 +77,7 @@ def _compile(src, obj, verbose):
 def build(force=False, verbose=False, jobs=None):
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
+    generate()
     hdr_time = max(os.path.getmtime(h) for h in headers())
     todo, objs = [], []
     for src in sources():
@@ -54,11 +85,38 @@ def build(force=False, verbose=False, jobs=None):
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
             todo.append((src, obj))
-    if todo:
+    # generated PTX kernels -> cubins, embedded as read-only data (symbol r0_cubin_<file stem>)
+    ptx_todo, cubins = [], []
+    for ptx in ptx_sources():
+        cubin = os.path.join(OBJ, os.path.basename(ptx)[:-4] + ".cubin")
+        cubins.append(cubin)
+        if force or not os.path.exists(cubin) or os.path.getmtime(cubin) < os.path.getmtime(ptx):
+            ptx_todo.append((ptx, cubin))
+    if todo or ptx_todo:
         with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
-            for src, log in ex.map(lambda so: _compile(so[0], so[1], verbose), todo):
+            futs = [ex.submit(_compile, s_, o_, verbose) for s_, o_ in todo]
+            futs += [ex.submit(_assemble, p_, c_, verbose) for p_, c_ in ptx_todo]
+            for f in futs:
+                src, log = f.result()
                 if verbose:
                     sys.stderr.write("== %s\n%s" % (os.path.basename(src), log))
+    if cubins:
+        embed_s = os.path.join(OBJ, "embed_cubins.S")
+        embed_o = os.path.join(OBJ, "embed_cubins.o")
+        text = ['.section .rodata']
+        for cubin in cubins:
+            sym = "r0_cubin_" + os.path.basename(cubin)[:-6]
+            text += [".global %s" % sym, ".balign 16", "%s:" % sym, '.incbin "%s"' % cubin]
+        text.append('.section .note.GNU-stack,"",@progbits')
+        new = "\n".join(text) + "\n"
+        if ptx_todo or not os.path.exists(embed_o) or not os.path.exists(embed_s) or open(embed_s).read() != new:
+            with open(embed_s, "w") as f:
+                f.write(new)
+            r = subprocess.run(["gcc", "-c", embed_s, "-o", embed_o], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("embedding cubins failed:\n%s" % r.stderr)
+            todo.append((embed_s, embed_o))
+        objs.append(embed_o)
     if todo or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -269,4 +269,18 @@ r0b200_err r0b200_combos_divide(r0b200_ctx* ctx, uint32_t* combos, size_t nchunk
   R0_API_END
 }
 
+r0b200_err r0b200_eval_check_rv32im(r0b200_ctx* ctx, uint32_t* check, const uint32_t* ctrl, const uint32_t* data,
+                                    const uint32_t* accum, const uint32_t* mix, const uint32_t* out,
+                                    const uint32_t* poly_mix_host, uint32_t po2) {
+  CTX_BEGIN
+  (void)ctrl;
+  // the Hal passes mix / out as device buffers; the kernels take them in the parameter block (constant bank)
+  uint32_t host[36 + 90];
+  R0_CUDA(cudaMemcpyAsync(host, mix, 36 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  R0_CUDA(cudaMemcpyAsync(host + 36, out, 90 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  R0_CUDA(cudaStreamSynchronize(ctx->stream));
+  r0_eval_check_rv32im(ctx, check, accum, data, host + 36, host, ext_from_host(poly_mix_host), po2);
+  R0_API_END
+}
+
 }  // extern "C"

@@ -37,5 +37,20 @@ void r0_combos_prepare(r0::Ctx* c, uint32_t* combos, const r0::FpExt* coeff_u_ho
                        uint32_t combo_count, size_t cycles, const uint32_t* reg_sizes, const uint32_t* reg_combo_ids,
                        uint32_t nregs, const r0::FpExt& mix, uint32_t check_size);
 void r0_poly_divide(r0::Ctx* c, uint32_t* poly, size_t n, const r0::FpExt& z, uint32_t* remainder_dev);
-void r0_gather_batched(r0::Ctx* c, uint32_t* dst, const void* jobs_host, size_t njobs);
-void r0_gather_digests(r0::Ctx* c, uint32_t* dst, const void* jobs_host, size_t njobs);
+// job j: dst[dst_off + g] = src[g * stride + idx] for g < size   (one MerkleTreeProver::prove column read)
+struct GatherJob {
+  const uint32_t* src;
+  uint64_t idx, stride;
+  uint32_t size, dst_off;
+};
+// dst[8*j .. 8*j+8) = nodes[8*idx ..]
+struct DigestJob {
+  const uint32_t* nodes;
+  uint64_t idx;
+};
+void r0_gather_batched(r0::Ctx* c, uint32_t* dst, const GatherJob* jobs_host, size_t njobs);
+void r0_gather_digests(r0::Ctx* c, uint32_t* dst, const DigestJob* jobs_host, size_t njobs);
+
+// generated circuit kernels (csrc/gen/, tools/gen_eval_check.py)
+void r0_eval_check_rv32im(r0::Ctx* c, uint32_t* check, const uint32_t* accum, const uint32_t* data,
+                          const uint32_t* global_host, const uint32_t* mix_host, const r0::FpExt& poly_mix, uint32_t po2);

@@ -12,6 +12,7 @@
 // coalesced or 128-bit vector accesses, products accumulated lazily in 64 bits (fp.cuh lazy_mac) so an
 // FpExt += Fp * FpExt costs four IMAD.WIDE instead of four full Montgomery products.
 #include "ctx.h"
+#include "launchers.h"
 
 namespace r0 {
 
@@ -175,20 +176,11 @@ __global__ void k_gather(uint32_t* dst, const uint32_t* src, size_t idx, size_t 
 }
 // Batched form used by the product driver: every opening of every query in one launch.
 // job j: dst[dst_off[j] + g] = src_j[g * stride_j + idx_j] for g < size_j
-struct GatherJob {
-  const uint32_t* src;
-  uint64_t idx, stride;
-  uint32_t size, dst_off;
-};
 __global__ void k_gather_batched(uint32_t* dst, const GatherJob* jobs) {
   const GatherJob j = jobs[blockIdx.x];
   for (uint32_t g = threadIdx.x; g < j.size; g += blockDim.x) dst[j.dst_off + g] = j.src[(size_t)g * j.stride + j.idx];
 }
 // digests: dst[8*j .. 8*j+8) = nodes_j[8*idx_j ..]
-struct DigestJob {
-  const uint32_t* nodes;
-  uint64_t idx;
-};
 __global__ void k_gather_digests(uint32_t* dst, const DigestJob* jobs, size_t njobs) {
   size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t j = w >> 3;
@@ -496,14 +488,14 @@ void r0_poly_divide(Ctx* c, uint32_t* poly, size_t n, const FpExt& z, uint32_t* 
 }
 
 // ---- batched query openings (product driver) ------------------------------------------------------------------
-void r0_gather_batched(Ctx* c, uint32_t* dst, const void* jobs_host, size_t njobs) {
+void r0_gather_batched(Ctx* c, uint32_t* dst, const GatherJob* jobs_host, size_t njobs) {
   if (njobs == 0) return;
   Scratch d_jobs(c, jobs_host, njobs * sizeof(GatherJob));
   k_gather_batched<<<(unsigned)njobs, 128, 0, c->stream>>>(dst, d_jobs.as<GatherJob>());
   count_launch(c);
   R0_CUDA(cudaGetLastError());
 }
-void r0_gather_digests(Ctx* c, uint32_t* dst, const void* jobs_host, size_t njobs) {
+void r0_gather_digests(Ctx* c, uint32_t* dst, const DigestJob* jobs_host, size_t njobs) {
   if (njobs == 0) return;
   Scratch d_jobs(c, jobs_host, njobs * sizeof(DigestJob));
   k_gather_digests<<<(unsigned)((njobs * 8 + 255) / 256), 256, 0, c->stream>>>(dst, d_jobs.as<DigestJob>(), njobs);

@@ -1,0 +1,452 @@
+// Segment prover driver: the callers of the Hal on the hot path (SURVEY §8f "callers either side"), i.e. what
+// `SegmentProverImpl::prove_core`'s prove_inner block does with a committed witness, as one stream-ordered C++ routine.
+//
+// Mirrors, op for op and in the same transcript order:
+//   risc0/circuit/rv32im/src/prove/hal/mod.rs:171-222   prove_core (header, group commits, mix draw, finalize)
+//   risc0/zkp/src/prove/prover.rs:38-48,81-108,111-393  make_coeffs, commit_group, finalize
+//   risc0/zkp/src/prove/poly_group.rs:63-83             PolyGroup::new
+//   risc0/zkp/src/prove/merkle.rs:54-138                MerkleTreeProver::{new, commit, prove}
+//   risc0/zkp/src/prove/fri.rs:39-126                   fri_prove
+//   risc0/zkp/src/taps.rs:21-342                        TapSet accessors
+//   risc0/zkp/src/core/poly.rs:38-89                    poly_interpolate (host, <= 6 points per register)
+// What is different from the reference's flow: the host only synchronises where Fiat-Shamir needs a digest or an
+// evaluation back (one small D2H per commitment); make_coeffs fuses interpolate + zk_shift; each Merkle tree is one
+// call; all 350 query openings are gathered by two launches after the 50 positions have been drawn (drawing them has
+// no side effects on the transcript other than the RNG itself, so the seal is unchanged).
+#include <algorithm>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/r0b200.h"
+#include "ctx.h"
+#include "launchers.h"
+#include "tables/circuit_rv32im.h"
+#include "tables/field_tables.h"
+#include "transcript.h"
+
+namespace r0 {
+namespace {
+
+constexpr size_t QUERIES = 50, INV_RATE = 4, FRI_FOLD = 16, FRI_MIN_DEGREE = 256, CHECK_SIZE = 16, EXT = 4;
+
+struct DevBuf {
+  Ctx* c = nullptr;
+  uint32_t* p = nullptr;
+  size_t words = 0;
+  DevBuf() {}
+  DevBuf(Ctx* c_, size_t words_) : c(c_), words(words_) {
+    R0_CUDA(cudaMallocAsync(&p, (words ? words : 4) * 4, c->stream));
+    c->bytes_allocated += words * 4;
+    if (c->bytes_allocated > c->bytes_peak) c->bytes_peak = c->bytes_allocated;
+  }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    release();
+    c = o.c;
+    p = o.p;
+    words = o.words;
+    o.p = nullptr;
+    return *this;
+  }
+  void release() {
+    if (p) {
+      cudaFreeAsync(p, c->stream);
+      c->bytes_allocated -= words * 4;
+      p = nullptr;
+    }
+  }
+  ~DevBuf() { release(); }
+};
+
+struct Tap {
+  uint16_t offset, back, group, combo, skip;
+};
+
+struct TapSet {
+  std::vector<Tap> taps;
+  std::vector<uint16_t> combo_taps, combo_begin;
+  std::vector<uint32_t> group_begin;
+  std::vector<uint32_t> group_sizes;
+  size_t combos_count = 0;
+  size_t num_groups() const { return group_begin.size() - 1; }
+  size_t tap_size() const { return group_begin.back(); }
+  std::vector<size_t> regs(size_t begin, size_t end) const {  // first tap of each register in [begin, end)
+    std::vector<size_t> r;
+    for (size_t cur = begin; cur < end; cur += taps[cur].skip) r.push_back(cur);
+    return r;
+  }
+};
+
+TapSet rv32im_taps() {
+  TapSet t;
+  for (size_t i = 0; i < RV32IM_NUM_TAPS; i++) {
+    const uint16_t* f = RV32IM_TAPS + 5 * i;
+    t.taps.push_back({f[0], f[1], f[2], f[3], f[4]});
+  }
+  t.combo_taps.assign(RV32IM_COMBO_TAPS, RV32IM_COMBO_TAPS + RV32IM_TOT_COMBO_BACKS);
+  t.combo_begin.assign(RV32IM_COMBO_BEGIN, RV32IM_COMBO_BEGIN + RV32IM_NUM_COMBOS + 1);
+  t.group_begin.assign(RV32IM_GROUP_BEGIN, RV32IM_GROUP_BEGIN + 4);
+  t.group_sizes.assign(RV32IM_GROUP_SIZES, RV32IM_GROUP_SIZES + 3);
+  t.combos_count = RV32IM_NUM_COMBOS;
+  return t;
+}
+
+size_t log2_exact(size_t n) {
+  size_t k = 0;
+  while ((size_t(1) << k) < n) k++;
+  R0_CHECK((size_t(1) << k) == n, "size is not a power of two");
+  return k;
+}
+
+// ---- host-side interpolation over <= 6 points (poly.rs:38-76); exact arithmetic makes the method irrelevant, so
+// this is plain Lagrange: out = sum_i fx[i] * prod_{j != i} (X - x_j) / (x_i - x_j)
+void poly_interpolate(FpExt* out, const FpExt* x, const FpExt* fx, size_t n) {
+  for (size_t k = 0; k < n; k++) out[k] = ext_zero();
+  std::vector<FpExt> basis(n);
+  for (size_t i = 0; i < n; i++) {
+    for (size_t k = 0; k < n; k++) basis[k] = ext_zero();
+    basis[0] = ext_one();
+    size_t deg = 0;
+    FpExt denom = ext_one();
+    for (size_t j = 0; j < n; j++) {
+      if (j == i) continue;
+      // basis *= (X - x_j)
+      for (size_t k = deg + 1; k-- > 0;) {
+        FpExt up = basis[k];
+        if (k + 1 < n) basis[k + 1] = ext_add(basis[k + 1], up);
+        basis[k] = ext_mul(up, ext_neg(x[j]));
+      }
+      deg++;
+      denom = ext_mul(denom, ext_sub(x[i], x[j]));
+    }
+    FpExt scale = ext_mul(fx[i], ext_inv(denom));
+    for (size_t k = 0; k < n; k++) out[k] = ext_add(out[k], ext_mul(scale, basis[k]));
+  }
+}
+
+struct Opening {  // one MerkleTreeProver::prove call, resolved after the batched gathers
+  size_t val_off, cols, dig_off, ndig;
+};
+
+struct Openings {
+  std::vector<GatherJob> vjobs;
+  std::vector<DigestJob> djobs;
+  std::vector<Opening> list;
+  size_t val_words = 0;
+};
+
+struct MerkleTree {
+  DevBuf nodes;
+  const uint32_t* matrix = nullptr;
+  size_t rows = 0, cols = 0, top_size = 0;
+  Digest root{};
+
+  MerkleTree() {}
+  MerkleTree(Ctx* c, int hash, const uint32_t* mat, size_t rows_, size_t cols_) : nodes(c, 2 * rows_ * 8), matrix(mat), rows(rows_), cols(cols_) {
+    size_t layers = log2_exact(rows);
+    size_t top_layer = 0;
+    for (size_t i = 1; i < layers; i++) {
+      if ((size_t(1) << i) > QUERIES) break;
+      top_layer = i;
+    }
+    top_size = size_t(1) << top_layer;
+    const char* e = r0b200_merkle_build((r0b200_ctx*)c, hash, nodes.p, matrix, rows, cols);
+    if (e) {
+      std::string msg(e);
+      r0b200_free_error(e);
+      throw std::runtime_error(msg);
+    }
+  }
+  // writes nodes[top_size .. 2*top_size) to the proof and commits the root (merkle.rs:83-96)
+  void commit(Ctx* c, Transcript& iop, std::vector<Digest>* roots) {
+    std::vector<uint32_t> top(8 * top_size);
+    {
+      // fetch nodes [1, 2*top_size) in one copy: node 1 is the root, the last top_size of them are the top layer
+      std::vector<uint32_t> head(8 * 2 * top_size);
+      R0_CUDA(cudaMemcpyAsync(head.data() + 8, nodes.p + 8, (2 * top_size - 1) * 32, cudaMemcpyDeviceToHost, c->stream));
+      R0_CUDA(cudaStreamSynchronize(c->stream));
+      memcpy(root.w, head.data() + 8, 32);
+      memcpy(top.data(), head.data() + 8 * top_size, 32 * top_size);
+    }
+    iop.write(top.data(), top.size());
+    iop.commit(root);
+    if (roots) roots->push_back(root);
+  }
+  void prove(Openings& o, size_t idx) const {  // merkle.rs:108-138
+    Opening op{o.val_words, cols, o.djobs.size(), 0};
+    o.vjobs.push_back(GatherJob{matrix, (uint64_t)idx, (uint64_t)rows, (uint32_t)cols, (uint32_t)o.val_words});
+    o.val_words += cols;
+    idx += rows;
+    while (idx >= 2 * top_size) {
+      size_t low = idx & 1;
+      idx >>= 1;
+      o.djobs.push_back(DigestJob{nodes.p, (uint64_t)(2 * idx + (1 - low))});
+      op.ndig++;
+    }
+    o.list.push_back(op);
+  }
+};
+
+struct PolyGroup {
+  DevBuf coeffs, evaluated;
+  MerkleTree merkle;
+  size_t count = 0;
+};
+
+class SegmentProver {
+ public:
+  SegmentProver(Ctx* c, int hash, size_t po2) : c_(c), hash_(hash), po2_(po2), cycles_(size_t(1) << po2), iop_(hash), suite_{hash}, taps_(rv32im_taps()) {
+    groups_.resize(taps_.num_groups());
+  }
+  Transcript& iop() { return iop_; }
+  std::vector<Digest> roots;
+  std::vector<uint32_t> query_pos;
+
+  // Prover::commit_group (prover.rs:81-108). `witness` may be a host or a device pointer.
+  void commit_group(size_t g, const uint32_t* witness, bool on_host) {
+    const size_t count = taps_.group_sizes[g];
+    PolyGroup& pg = groups_[g];
+    pg.count = count;
+    pg.coeffs = DevBuf(c_, count * cycles_);
+    if (on_host) {
+      R0_CUDA(cudaMemcpyAsync(pg.coeffs.p, witness, count * cycles_ * 4, cudaMemcpyHostToDevice, c_->stream));
+    } else {
+      r0_eltwise_copy(c_, pg.coeffs.p, witness, count * cycles_);
+    }
+    r0_ntt_interpolate(c_, pg.coeffs.p, count, (int)po2_, /*zk=*/true, 0);
+    finish_group(pg);
+    pg.merkle.commit(c_, iop_, &roots);
+  }
+
+  // Prover::finalize (prover.rs:111-393); globals: mix (36 words) and out (90 words), host Montgomery words
+  void finalize(const uint32_t* mix_host, const uint32_t* out_host) {
+    const size_t domain = cycles_ * INV_RATE;
+    const FpExt poly_mix = iop_.random_ext();
+    PolyGroup check;
+    check.count = CHECK_SIZE;
+    check.coeffs = DevBuf(c_, EXT * domain);
+    r0_eval_check_rv32im(c_, check.coeffs.p, groups_[0].evaluated.p, groups_[2].evaluated.p, out_host, mix_host, poly_mix,
+                         (uint32_t)po2_);
+    r0_ntt_interpolate(c_, check.coeffs.p, EXT, (int)(po2_ + 2), /*zk=*/false, 0);
+    finish_group(check);
+    check.merkle.commit(c_, iop_, &roots);
+
+    const FpExt z = iop_.random_ext();
+    const FpExt back_one = ext_from_fp(R0_ROU_REV_MONT[po2_]);
+    // evaluate every tap at z * back_one^back (prover.rs:176-211)
+    const size_t ntaps = taps_.tap_size();
+    std::vector<FpExt> all_xs(ntaps), eval_u(ntaps + CHECK_SIZE);
+    std::vector<uint32_t> which(ntaps + CHECK_SIZE);
+    for (size_t t = 0; t < ntaps; t++) {
+      which[t] = taps_.taps[t].offset;
+      all_xs[t] = ext_mul(ext_pow(back_one, taps_.taps[t].back), z);
+    }
+    const FpExt z_pow = ext_pow(z, EXT);
+    for (size_t i = 0; i < CHECK_SIZE; i++) which[ntaps + i] = (uint32_t)i;
+    {
+      std::vector<FpExt> xs(all_xs);
+      xs.resize(ntaps + CHECK_SIZE, z_pow);
+      DevBuf d_which(c_, which.size()), d_xs(c_, xs.size() * 4), d_out(c_, xs.size() * 4);
+      R0_CUDA(cudaMemcpyAsync(d_which.p, which.data(), which.size() * 4, cudaMemcpyHostToDevice, c_->stream));
+      R0_CUDA(cudaMemcpyAsync(d_xs.p, xs.data(), xs.size() * 16, cudaMemcpyHostToDevice, c_->stream));
+      for (size_t g = 0; g <= groups_.size(); g++) {
+        const size_t b = g < groups_.size() ? taps_.group_begin[g] : ntaps;
+        const size_t e = g < groups_.size() ? taps_.group_begin[g + 1] : ntaps + CHECK_SIZE;
+        const PolyGroup& pg = g < groups_.size() ? groups_[g] : check;
+        r0_batch_evaluate_any(c_, pg.coeffs.p, cycles_, d_which.p + b, d_xs.p + 4 * b, d_out.p + 4 * b, e - b);
+      }
+      R0_CUDA(cudaMemcpyAsync(eval_u.data(), d_out.p, eval_u.size() * 16, cudaMemcpyDeviceToHost, c_->stream));
+      R0_CUDA(cudaStreamSynchronize(c_->stream));
+    }
+    // coeff_u: per-register interpolation, then the 16 check evaluations verbatim (prover.rs:213-246)
+    std::vector<FpExt> coeff_u(ntaps + CHECK_SIZE);
+    const std::vector<size_t> regs = taps_.regs(0, ntaps);
+    for (size_t r : regs) poly_interpolate(&coeff_u[r], &all_xs[r], &eval_u[r], taps_.taps[r].skip);
+    for (size_t i = 0; i < CHECK_SIZE; i++) coeff_u[ntaps + i] = eval_u[ntaps + i];
+    iop_.write((const uint32_t*)coeff_u.data(), coeff_u.size() * 4);
+    iop_.commit(suite_.hash_words((const uint32_t*)coeff_u.data(), coeff_u.size() * 4));
+
+    // DEEP combination (prover.rs:248-352)
+    const FpExt mix = iop_.random_ext();
+    const size_t combo_count = taps_.combos_count;
+    DevBuf combos(c_, EXT * cycles_ * (combo_count + 1));
+    r0_fill(c_, combos.p, 0, combos.words);
+    FpExt cur_mix = ext_one();
+    for (size_t g = 0; g < groups_.size(); g++) {
+      const size_t gsize = taps_.group_sizes[g];
+      std::vector<uint32_t> ids;
+      for (size_t r : taps_.regs(taps_.group_begin[g], taps_.group_begin[g + 1])) ids.push_back(taps_.taps[r].combo);
+      R0_CHECK(ids.size() == gsize, "tap set: register count != group size");
+      r0_mix_poly_coeffs(c_, combos.p, cur_mix, mix, groups_[g].coeffs.p, ids.data(), gsize, cycles_);
+      cur_mix = ext_mul(cur_mix, ext_pow(mix, gsize));
+    }
+    {
+      std::vector<uint32_t> ids(CHECK_SIZE, (uint32_t)combo_count);
+      r0_mix_poly_coeffs(c_, combos.p, cur_mix, mix, check.coeffs.p, ids.data(), CHECK_SIZE, cycles_);
+    }
+    {
+      std::vector<uint32_t> reg_sizes, reg_ids;
+      for (size_t r : regs) {
+        reg_sizes.push_back(taps_.taps[r].skip);
+        reg_ids.push_back(taps_.taps[r].combo);
+      }
+      r0_combos_prepare(c_, combos.p, coeff_u.data(), coeff_u.size(), (uint32_t)combo_count, cycles_, reg_sizes.data(),
+                        reg_ids.data(), (uint32_t)reg_sizes.size(), mix, (uint32_t)CHECK_SIZE);
+      std::vector<uint32_t> pow_begin{0};
+      std::vector<uint32_t> pows;
+      auto push = [&](const FpExt& e) { pows.insert(pows.end(), e.c, e.c + 4); };
+      for (size_t i = 0; i < combo_count; i++) {
+        for (size_t k = taps_.combo_begin[i]; k < taps_.combo_begin[i + 1]; k++)
+          push(ext_mul(z, ext_pow(back_one, taps_.combo_taps[k])));
+        pow_begin.push_back((uint32_t)(pows.size() / 4));
+      }
+      push(z_pow);
+      pow_begin.push_back((uint32_t)(pows.size() / 4));
+      const char* e = r0b200_combos_divide((r0b200_ctx*)c_, combos.p, combo_count + 1, pow_begin.data(), pows.data(), cycles_);
+      if (e) {
+        std::string msg(e);
+        r0b200_free_error(e);
+        throw std::runtime_error(msg);
+      }
+    }
+    DevBuf final_coeffs(c_, EXT * cycles_);
+    r0_eltwise_sum_ext(c_, final_coeffs.p, combos.p, cycles_, combo_count + 1);
+    combos.release();
+    r0_bit_reverse(c_, final_coeffs.p, EXT, (int)po2_);
+    fri_prove(std::move(final_coeffs), check);
+  }
+
+ private:
+  // PolyGroup::new (poly_group.rs:63-83): LDE, coefficient bit reversal, Merkle tree over the evaluations
+  void finish_group(PolyGroup& pg) {
+    const size_t domain = cycles_ * INV_RATE;
+    pg.evaluated = DevBuf(c_, pg.count * domain);
+    r0_ntt_expand_evaluate(c_, pg.evaluated.p, pg.coeffs.p, pg.count, (int)(po2_ + 2), 2, 0);
+    r0_bit_reverse(c_, pg.coeffs.p, pg.count, (int)po2_);
+    pg.merkle = MerkleTree(c_, hash_, pg.evaluated.p, domain, pg.count);
+  }
+
+  struct FriRound {
+    size_t domain;
+    DevBuf evaluated, coeffs;
+    MerkleTree merkle;
+  };
+
+  void fri_prove(DevBuf&& in_coeffs, const PolyGroup& check) {  // fri.rs:77-126
+    const size_t orig_domain = in_coeffs.words / EXT * INV_RATE;
+    std::vector<std::unique_ptr<FriRound>> rounds;
+    DevBuf first = std::move(in_coeffs);
+    const DevBuf* coeffs = &first;
+    while (coeffs->words / EXT > FRI_MIN_DEGREE) {
+      std::unique_ptr<FriRound> r(new FriRound());
+      const size_t size = coeffs->words / EXT;
+      r->domain = size * INV_RATE;
+      r->evaluated = DevBuf(c_, r->domain * EXT);
+      r0_ntt_expand_evaluate(c_, r->evaluated.p, coeffs->p, EXT, (int)log2_exact(r->domain), 2, 0);
+      r->merkle = MerkleTree(c_, hash_, r->evaluated.p, r->domain / FRI_FOLD, FRI_FOLD * EXT);
+      r->merkle.commit(c_, iop_, &roots);
+      const FpExt fold_mix = iop_.random_ext();
+      r->coeffs = DevBuf(c_, size / FRI_FOLD * EXT);
+      r0_fri_fold(c_, r->coeffs.p, coeffs->p, size / FRI_FOLD, fold_mix);
+      rounds.push_back(std::move(r));
+      coeffs = &rounds.back()->coeffs;
+    }
+    {
+      DevBuf fin(c_, coeffs->words);
+      r0_eltwise_copy(c_, fin.p, coeffs->p, coeffs->words);
+      r0_bit_reverse(c_, fin.p, EXT, (int)log2_exact(coeffs->words / EXT));
+      std::vector<uint32_t> host(coeffs->words);
+      R0_CUDA(cudaMemcpyAsync(host.data(), fin.p, host.size() * 4, cudaMemcpyDeviceToHost, c_->stream));
+      R0_CUDA(cudaStreamSynchronize(c_->stream));
+      iop_.write(host.data(), host.size());
+      iop_.commit(suite_.hash_words(host.data(), host.size()));
+    }
+    // queries: positions first (RNG only), then every opening in two gathers
+    Openings o;
+    const unsigned bits = (unsigned)log2_exact(orig_domain);
+    for (size_t q = 0; q < QUERIES; q++) {
+      size_t pos = iop_.random_bits(bits);
+      query_pos.push_back((uint32_t)pos);
+      for (auto& g : groups_) g.merkle.prove(o, pos);
+      check.merkle.prove(o, pos);
+      for (auto& r : rounds) {
+        size_t group = pos % (r->domain / FRI_FOLD);
+        r->merkle.prove(o, group);
+        pos = group;
+      }
+    }
+    DevBuf d_vals(c_, o.val_words), d_digs(c_, o.djobs.size() * 8);
+    r0_gather_batched(c_, d_vals.p, o.vjobs.data(), o.vjobs.size());
+    r0_gather_digests(c_, d_digs.p, o.djobs.data(), o.djobs.size());
+    std::vector<uint32_t> vals(o.val_words), digs(o.djobs.size() * 8);
+    R0_CUDA(cudaMemcpyAsync(vals.data(), d_vals.p, vals.size() * 4, cudaMemcpyDeviceToHost, c_->stream));
+    R0_CUDA(cudaMemcpyAsync(digs.data(), d_digs.p, digs.size() * 4, cudaMemcpyDeviceToHost, c_->stream));
+    R0_CUDA(cudaStreamSynchronize(c_->stream));
+    for (const Opening& op : o.list) {
+      iop_.write(vals.data() + op.val_off, op.cols);
+      iop_.write(digs.data() + 8 * op.dig_off, 8 * op.ndig);
+    }
+  }
+
+  Ctx* c_;
+  int hash_;
+  size_t po2_, cycles_;
+  Transcript iop_;
+  HostSuite suite_;
+  TapSet taps_;
+  std::vector<PolyGroup> groups_;
+};
+
+}  // namespace
+}  // namespace r0
+
+using namespace r0;
+
+extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* code,
+                                          const uint32_t* data, const uint32_t* accum, int witness_on_host,
+                                          const uint32_t* global_host, uint32_t* seal_out_host, size_t seal_cap,
+                                          size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
+                                          uint32_t* query_pos_out_host) {
+  R0_API_BEGIN
+  R0_CHECK(ctx != nullptr, "null r0b200 context");
+  R0_CUDA(cudaSetDevice(ctx->device));
+  R0_CHECK(hash == R0B200_HASH_POSEIDON2 || hash == R0B200_HASH_SHA256, "prove: unknown hash suite");
+  R0_CHECK(po2 >= 9 && po2 + 2 <= (uint32_t)MAX_LG, "prove: po2 out of range (ZK_CYCLES = 1024 needs po2 >= 9... <= 22)");
+  SegmentProver prover(ctx, hash, po2);
+  Transcript& iop = prover.iop();
+  HostSuite suite{hash};
+  const uint32_t version = RV32IM_SEAL_VERSION;
+  iop.write(&version, 1);
+  auto commit_info = [&](const char* s) {
+    uint32_t e[16];
+    for (int i = 0; i < 16; i++) e[i] = fp_encode((uint32_t)(uint8_t)s[i]);
+    iop.commit(suite.hash_words(e, 16));
+  };
+  commit_info("RISC0_STARK:v1__");
+  commit_info(RV32IM_CIRCUIT_INFO);
+  // header: globals (INVALID -> 0) followed by the raw po2 word (rv32im/src/prove/hal/mod.rs:196-206)
+  uint32_t header[RV32IM_OUTPUT_SIZE + 1];
+  for (size_t i = 0; i < RV32IM_OUTPUT_SIZE; i++) header[i] = global_host[i] == FP_INVALID ? 0u : global_host[i];
+  header[RV32IM_OUTPUT_SIZE] = po2;
+  iop.commit(suite.hash_words(header, RV32IM_OUTPUT_SIZE + 1));
+  iop.write(header, RV32IM_OUTPUT_SIZE + 1);
+  prover.commit_group(1, code, witness_on_host != 0);
+  prover.commit_group(2, data, witness_on_host != 0);
+  uint32_t mix[RV32IM_MIX_SIZE];
+  for (size_t i = 0; i < RV32IM_MIX_SIZE; i++) mix[i] = iop.random_elem();
+  prover.commit_group(0, accum, witness_on_host != 0);
+  prover.finalize(mix, header);
+  R0_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (seal_len) *seal_len = iop.proof.size();
+  R0_CHECK(seal_out_host != nullptr && iop.proof.size() <= seal_cap, "prove: seal buffer too small");
+  memcpy(seal_out_host, iop.proof.data(), iop.proof.size() * 4);
+  if (nroots) *nroots = prover.roots.size();
+  if (roots_out_host) {
+    R0_CHECK(prover.roots.size() <= roots_cap, "prove: roots buffer too small");
+    memcpy(roots_out_host, prover.roots.data(), prover.roots.size() * 32);
+  }
+  if (query_pos_out_host) memcpy(query_pos_out_host, prover.query_pos.data(), prover.query_pos.size() * 4);
+  R0_API_END
+}

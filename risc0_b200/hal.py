@@ -292,3 +292,49 @@ class B200Hal:
         pows = _u32(pows if pows else [0, 0, 0, 0])
         check(self._l.r0b200_combos_divide(self._ctx, combos.ptr, C.c_size_t(len(chunks)), _np_ptr(_u32(pow_begin)),
                                            _np_ptr(pows), C.c_size_t(cycles)))
+
+    # ---- CircuitHal (hal/mod.rs:265-290) for rv32im
+    def eval_check_rv32im(self, check_buf, groups, globals_, poly_mix, po2, steps):
+        """groups = [accum, code, data] evaluated buffers (tap-group order); globals_ = [mix, out] device buffers
+        (the order rv32im/src/prove/hal/mod.rs:216 passes them)"""
+        assert steps == 1 << po2 and check_buf.size() == 16 * steps
+        accum, code, data = groups
+        mix, out = globals_
+        err = self._l.r0b200_eval_check_rv32im(self._ctx, check_buf.ptr, code.ptr, data.ptr, accum.ptr, mix.ptr,
+                                                     out.ptr, _np_ptr(_u32(poly_mix)), C.c_uint32(po2))
+        check(err)
+
+
+class SegmentProver:
+    """Host-side mirror of `SegmentProver::prove_core`'s prove_inner block for rv32im
+    (risc0/circuit/rv32im/src/prove/hal/mod.rs:171-222) over r0b200_prove_rv32im: commit code/data/accum, eval_check,
+    DEEP, FRI -> seal. `witness` arrays are column-major Montgomery words (numpy = host memory, Buffer = device)."""
+
+    def __init__(self, hal):
+        self.hal = hal
+        self.seal_cap = 1 << 20
+        self._seal = np.zeros(self.seal_cap, dtype=np.uint32)
+        self._roots = np.zeros(8 * 16, dtype=np.uint32)
+        self._qpos = np.zeros(50, dtype=np.uint32)
+
+    def prove(self, po2, code, data, accum, glob):
+        """returns (seal words, committed roots [k, 8], drawn query positions [50])"""
+        hal = self.hal
+        on_host = isinstance(data, np.ndarray)
+        n = 1 << po2
+        if on_host:
+            code, data, accum = _u32(code), _u32(data), _u32(accum)
+            assert code.size == n and data.size == 211 * n and accum.size == 103 * n
+            ptrs = [_np_ptr(code), _np_ptr(data), _np_ptr(accum)]
+        else:
+            assert code.size() == n and data.size() == 211 * n and accum.size() == 103 * n
+            ptrs = [code.ptr, data.ptr, accum.ptr]
+        glob = _u32(glob)
+        assert glob.size == 90
+        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
+        check(hal._l.r0b200_prove_rv32im(hal._ctx, hal.hash, C.c_uint32(po2), ptrs[0], ptrs[1], ptrs[2],
+                                         C.c_int(1 if on_host else 0), _np_ptr(glob), _np_ptr(self._seal),
+                                         C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots),
+                                         C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
+        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
+                self._qpos.copy())

@@ -251,6 +251,13 @@ def scatter(into, index, offsets, values):
     return into
 
 
+def eltwise_copy_elem_slice(into, frm, from_rows, from_cols, from_offset, from_stride, into_offset, into_stride):
+    into = u32(into).copy()
+    lib().orc_eltwise_copy_elem_slice(ptr(into), ptr(u32(frm)), _u64(from_rows), _u64(from_cols), _u64(from_offset),
+                                      _u64(from_stride), _u64(into_offset), _u64(into_stride))
+    return into
+
+
 def prefix_products(io):
     io = u32(io).copy()
     lib().orc_prefix_products(ptr(io), _u64(len(io) // 4))

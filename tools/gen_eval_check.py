@@ -1,0 +1,885 @@
+#!/usr/bin/env python3
+"""Back end of the eval_check code generator: lowers the constraint DAG built by tools/circuit_ir.py to 32-bit
+scalar operations, schedules them and emits sm_100a PTX (risc0_b200/csrc/gen/eval_check_<circuit>_p<j>.ptx, assembled
+by ptxas and embedded in libr0b200.so by risc0_b200/build.py) plus the host launcher (eval_check_<circuit>.cu).
+
+    python tools/gen_eval_check.py rv32im            # needs /root/reference OR the committed IR
+    python tools/gen_eval_check.py rv32im --from-ir  # rebuild from risc0_b200/circuits/rv32im.ir.json.gz only
+
+What the kernel computes is CircuitHal::eval_check (risc0/zkp/src/hal/mod.rs:279-289; CPU spec
+risc0/circuit/rv32im/src/prove/hal/cpu.rs:145-208): for every point i of the 4N domain,
+    check[k*D + i] = (poly_fp(i) * ((3 * w_4N^i)^N - 1)^-1)[k].
+How it is computed differs from both reference back ends (DESIGN.md "eval_check"):
+  * one flat DAG (common sub-expressions merged across the reference's 21 sub-functions), scheduled depth-first with
+    the heavier operand first so that live ranges stay short;
+  * every `acc + v * poly_mix[k]` chain is flattened into a sum of products and evaluated with lazy 64-bit
+    multiply-accumulate (one IMAD.WIDE per term and component, one Montgomery reduction per chain) - exact
+    arithmetic makes any re-association bit-identical;
+  * poly_mix powers (and their -11 multiples for the X^4 = -11 wrap) sit in the constant bank, so they are free operands;
+  * the divisor only takes 4 values ((3w^i)^N = 3^N * w_4^(i mod 4)): its inverses are computed once on the host.
+"""
+import gzip
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import circuit_ir as ir  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = ir.P
+R = 2**32 % P
+FP, EXT = ir.FP, ir.EXT
+
+
+def mont(x):
+    return (x % P) * R % P
+
+
+CIRCUITS = {
+    "rv32im": dict(
+        srcs=["/root/reference/risc0/circuit/rv32im-sys/kernels/cxx/rust_poly_fp_%d.cpp" % i for i in range(4)],
+        arg_names=("accum", "data", "global", "mix"),
+        cols=dict(accum=103, data=211, code=1),
+        n_global=90, n_mix=36,
+    ),
+}
+
+
+# ------------------------------------------------------------------------------------------------ IR (de)serialise
+def save_ir(dag, path):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with gzip.open(path, "wt") as f:
+        json.dump(dict(nodes=[list(k) for k in dag.nodes], types=dag.types, root=dag.root), f, separators=(",", ":"))
+
+
+def load_ir(path):
+    with gzip.open(path, "rt") as f:
+        d = json.load(f)
+    dag = ir.Dag()
+    dag.nodes = [tuple(k) for k in d["nodes"]]
+    dag.types = d["types"]
+    dag.root = d["root"]
+    return dag
+
+
+# ------------------------------------------------------------------------------------------------ scheduling
+def schedule(dag):
+    """post-order DFS from the root, heavier operand first (Sethi-Ullman flavour). Returns node ids in emit order."""
+    n = len(dag.nodes)
+    weight = [1] * n
+    for i, k in enumerate(dag.nodes):  # ids are topologically ordered by construction (operands before users)
+        if k[0] in "+-*":
+            weight[i] = 1 + weight[k[1]] + weight[k[2]]
+    order, seen = [], [False] * n
+    stack = [(dag.root, False)]
+    while stack:
+        node, done = stack.pop()
+        if done:
+            order.append(node)
+            continue
+        if seen[node]:
+            continue
+        seen[node] = True
+        stack.append((node, True))
+        k = dag.nodes[node]
+        if k[0] in "+-*":
+            a, b = k[1], k[2]
+            first, second = (a, b) if weight[a] >= weight[b] else (b, a)
+            stack.append((second, False))
+            stack.append((first, False))
+    return order
+
+
+def flatten_sum(dag, uses):
+    """top-level terms of the root: root = sum(terms) (ext additions used once are folded into the sum)"""
+    terms, st = [], [dag.root]
+    while st:
+        n = st.pop()
+        k = dag.nodes[n]
+        if k[0] == "+" and dag.types[n] == EXT and dag.types[k[1]] == EXT and dag.types[k[2]] == EXT and (
+                n == dag.root or uses[n] == 1):
+            st.append(k[2])
+            st.append(k[1])
+        else:
+            terms.append(n)
+    return terms
+
+
+def reach(dag, roots):
+    seen, st = set(), list(roots)
+    while st:
+        x = st.pop()
+        if x in seen:
+            continue
+        seen.add(x)
+        k = dag.nodes[x]
+        if k[0] in "+-*":
+            st.append(k[1])
+            st.append(k[2])
+    return seen
+
+
+def node_cost(dag, x):
+    k = dag.nodes[x]
+    if k[0] == "t":
+        return 1
+    if k[0] not in "+-*":
+        return 0
+    if dag.types[x] == FP:
+        return 1
+    return 16 if (k[0] == "*" and dag.types[k[1]] == EXT and dag.types[k[2]] == EXT) else 4
+
+
+def partition(dag, uses, nparts):
+    """split the top-level sum into `nparts` groups of terms with balanced cost; sub-expressions shared between
+    groups are recomputed in each (about a quarter of the work for 75 single-term groups, less when binned)."""
+    terms = flatten_sum(dag, uses)
+    info = []
+    for t in terms:
+        r = reach(dag, [t])
+        info.append((sum(node_cost(dag, x) for x in r), t, r))
+    info.sort(key=lambda z: -z[0])
+    bins = [dict(terms=[], nodes=set(), cost=0) for _ in range(nparts)]
+    for c, t, r in info:
+        best, best_cost = None, None
+        for b in bins:
+            extra = sum(node_cost(dag, x) for x in r - b["nodes"])
+            tot = b["cost"] + extra
+            if best is None or tot < best_cost:
+                best, best_cost = b, tot
+        best["terms"].append(t)
+        best["cost"] = best_cost
+        best["nodes"] |= r
+    return [b for b in bins if b["terms"]]
+
+
+def schedule_part(dag, terms):
+    """like schedule() but for a set of roots; returns emit order"""
+    n = len(dag.nodes)
+    weight = [1] * n
+    for i, k in enumerate(dag.nodes):
+        if k[0] in "+-*":
+            weight[i] = 1 + weight[k[1]] + weight[k[2]]
+    order, seen = [], set()
+    for root in terms:
+        stack = [(root, False)]
+        while stack:
+            node, done = stack.pop()
+            if done:
+                order.append(node)
+                continue
+            if node in seen:
+                continue
+            seen.add(node)
+            stack.append((node, True))
+            k = dag.nodes[node]
+            if k[0] in "+-*":
+                a, b = k[1], k[2]
+                first, second = (a, b) if weight[a] >= weight[b] else (b, a)
+                stack.append((second, False))
+                stack.append((first, False))
+    return order
+
+
+# ------------------------------------------------------------------------------------------------ scalar lowering
+NINV = 0x77FFFFFF            # -P^-1 mod 2^32
+MONT_ONE = R
+RINV = pow(R, -1, P)
+NBETA_M = mont(P - 11)
+
+
+def mont_mul(a, b):
+    return a * b * RINV % P
+
+
+class Scalars:
+    """hash-consed DAG of 32-bit field operations (every value canonical Montgomery, < P)"""
+
+    def __init__(self):
+        self.nodes, self.index = [], {}
+
+    def add_node(self, key):
+        i = self.index.get(key)
+        if i is None:
+            i = len(self.nodes)
+            self.nodes.append(key)
+            self.index[key] = i
+        return i
+
+    def imm(self, v):
+        return self.add_node(("i", v % P))
+
+    def cst(self, off):
+        return self.add_node(("k", off))
+
+    def tap(self, buf, col, back):
+        return self.add_node(("t", buf, col, back))
+
+    def is_imm(self, a, v=None):
+        k = self.nodes[a]
+        return k[0] == "i" and (v is None or k[1] == v)
+
+    def add(self, a, b):
+        if self.is_imm(a, 0):
+            return b
+        if self.is_imm(b, 0):
+            return a
+        if self.is_imm(a) and self.is_imm(b):
+            return self.imm(self.nodes[a][1] + self.nodes[b][1])
+        if a > b:
+            a, b = b, a
+        return self.add_node(("+", a, b))
+
+    def sub(self, a, b):
+        if self.is_imm(b, 0):
+            return a
+        if a == b:
+            return self.imm(0)
+        if self.is_imm(a) and self.is_imm(b):
+            return self.imm(self.nodes[a][1] - self.nodes[b][1])
+        if self.is_imm(a, 0):
+            return self.add_node(("n", b))
+        return self.add_node(("-", a, b))
+
+    def neg(self, a):
+        return self.sub(self.imm(0), a)
+
+    def mul(self, a, b):
+        if self.is_imm(a, 0) or self.is_imm(b, 0):
+            return self.imm(0)
+        if self.is_imm(a, MONT_ONE):
+            return b
+        if self.is_imm(b, MONT_ONE):
+            return a
+        if self.is_imm(a) and self.is_imm(b):
+            return self.imm(mont_mul(self.nodes[a][1], self.nodes[b][1]))
+        if a > b:
+            a, b = b, a
+        return self.add_node(("*", a, b))
+
+    def dot(self, terms):
+        terms = [(min(a, b), max(a, b)) for a, b in terms if not (self.is_imm(a, 0) or self.is_imm(b, 0))]
+        if not terms:
+            return self.imm(0)
+        if len(terms) == 1:
+            return self.mul(*terms[0])
+        return self.add_node(("d", tuple(sorted(terms))))
+
+    def operands(self, i):
+        k = self.nodes[i]
+        if k[0] in "+-*":
+            return [k[1], k[2]]
+        if k[0] in ("n", "N"):
+            return [k[1]]
+        if k[0] == "d":
+            return [x for ab in k[1] for x in ab]
+        return []
+
+
+class Layout:
+    """byte offsets inside the kernel's constant parameter block"""
+
+    def __init__(self, npm, n_global, n_mix):
+        self.pm = 0
+        self.npm = 16 * npm
+        self.glob = 32 * npm
+        self.mix = self.glob + 4 * n_global
+        self.inv_y = self.mix + 4 * n_mix
+        self.size = self.inv_y + 16
+        self.n = npm
+
+
+def lower(dag, terms, lay):
+    """ext-level DAG -> scalar DAG; returns (Scalars, [4 output scalars])"""
+    S = Scalars()
+    memo = {}
+    zero = S.imm(0)
+
+    def nbeta_of(s):
+        k = S.nodes[s]
+        if k[0] == "k" and lay.pm <= k[1] < lay.npm:
+            return S.cst(k[1] + lay.npm)       # the precomputed (-11 * pm[k][c]) copy
+        return S.mul(s, S.imm(NBETA_M))
+
+    def ext_mul(x, y):
+        # prefer the side made of constants as `y` so that its -11 multiples are free
+        def constness(v):
+            return sum(1 for s in v if S.nodes[s][0] in "ik")
+        if constness(x) > constness(y):
+            x, y = y, x
+        nb, nc, nd = nbeta_of(y[1]), nbeta_of(y[2]), nbeta_of(y[3])
+        return (S.dot([(x[0], y[0]), (x[1], nd), (x[2], nc), (x[3], nb)]),
+                S.dot([(x[0], y[1]), (x[1], y[0]), (x[2], nd), (x[3], nc)]),
+                S.dot([(x[0], y[2]), (x[1], y[1]), (x[2], y[0]), (x[3], nd)]),
+                S.dot([(x[0], y[3]), (x[1], y[2]), (x[2], y[1]), (x[3], y[0])]))
+
+    def get(n):
+        """iterative post-order evaluation; FP nodes -> scalar id, EXT nodes -> 4-tuple"""
+        stack = [n]
+        while stack:
+            cur = stack[-1]
+            if cur in memo:
+                stack.pop()
+                continue
+            k = dag.nodes[cur]
+            o = k[0]
+            if o in "+-*":
+                pend = [x for x in (k[1], k[2]) if x not in memo]
+                if pend:
+                    stack.extend(pend)
+                    continue
+                a, b = memo[k[1]], memo[k[2]]
+                ea, eb = isinstance(a, tuple), isinstance(b, tuple)
+                if not ea and not eb:
+                    r = {"+": S.add, "-": S.sub, "*": S.mul}[o](a, b)
+                elif ea and eb:
+                    if o == "*":
+                        r = ext_mul(a, b)
+                    else:
+                        f = S.add if o == "+" else S.sub
+                        r = tuple(f(a[c], b[c]) for c in range(4))
+                elif o == "*":
+                    e, f = (a, b) if ea else (b, a)
+                    r = tuple(S.mul(e[c], f) for c in range(4))
+                elif o == "+":
+                    e, f = (a, b) if ea else (b, a)
+                    r = (S.add(e[0], f), e[1], e[2], e[3])
+                elif ea:   # ext - fp
+                    r = (S.sub(a[0], b), a[1], a[2], a[3])
+                else:      # fp - ext
+                    r = (S.sub(a, b[0]), S.neg(b[1]), S.neg(b[2]), S.neg(b[3]))
+            elif o == "c":
+                r = S.imm(mont(k[1]))
+            elif o == "ce":
+                r = tuple(S.imm(mont(v)) for v in k[1:5])
+            elif o == "pm":
+                r = tuple(S.cst(lay.pm + 16 * k[1] + 4 * c) for c in range(4))
+            elif o == "g":
+                base = lay.glob if k[1] == "global" else lay.mix
+                r = S.cst(base + 4 * k[2])
+            elif o == "t":
+                r = S.tap(k[1], k[2], k[3])
+            else:
+                raise ValueError(k)
+            memo[cur] = r
+            stack.pop()
+        return memo[n]
+
+    tot = [zero] * 4
+    for t in terms:
+        v = get(t)
+        if not isinstance(v, tuple):
+            v = (v, zero, zero, zero)
+        tot = [S.add(tot[c], v[c]) for c in range(4)]
+    return S, tot
+
+
+def flatten_sums(S, outs):
+    """v2 optimisation: turn single-use add/sub trees (leaves: single-use products or plain values) into one lazy
+    64-bit dot product. Exact arithmetic -> identical results. Returns (new Scalars, new outs)."""
+    n = len(S.nodes)
+    uses = [0] * n
+    for i in range(n):
+        for o in S.operands(i):
+            uses[o] += 1
+    for o in outs:
+        uses[o] += 1
+    T = Scalars()
+    memo = {}
+    one = ("i", MONT_ONE)
+
+    def leaves(root):
+        """[(sign, node)] of the maximal single-use add/sub tree under root"""
+        out, st = [], [(1, root, True)]
+        while st:
+            sg, x, is_root = st.pop()
+            k = S.nodes[x]
+            if (is_root or uses[x] == 1) and k[0] in "+-":
+                st.append((sg, k[1], False))
+                st.append((sg if k[0] == "+" else -sg, k[2], False))
+            elif (is_root or uses[x] == 1) and k[0] == "n":
+                st.append((-sg, k[1], False))
+            else:
+                out.append((sg, x))
+        return out
+
+    def conv(root):
+        stack = [root]
+        while stack:
+            cur = stack[-1]
+            if cur in memo:
+                stack.pop()
+                continue
+            k = S.nodes[cur]
+            lv = leaves(cur) if k[0] in "+-n" else []
+            if len(lv) >= 3:
+                # product leaves used once are folded in as terms; their operands are what we need converted
+                need = []
+                for sg, x in lv:
+                    kx = S.nodes[x]
+                    if uses[x] == 1 and kx[0] in "*d":
+                        need.extend(S.operands(x))
+                    else:
+                        need.append(x)
+                pend = [x for x in need if x not in memo]
+                if pend:
+                    stack.extend(pend)
+                    continue
+                terms = []
+                for sg, x in lv:
+                    kx = S.nodes[x]
+                    if uses[x] == 1 and kx[0] == "*":
+                        prods = [(memo[kx[1]], memo[kx[2]])]
+                    elif uses[x] == 1 and kx[0] == "d":
+                        prods = [(memo[a], memo[b]) for a, b in kx[1]]
+                    else:
+                        prods = [(memo[x], T.imm(MONT_ONE))]
+                    for a, b in prods:
+                        if sg < 0:
+                            # negate the cheaper side: an immediate is free, otherwise one subtraction
+                            if T.is_imm(b):
+                                b = T.imm(-T.nodes[b][1])
+                            elif T.is_imm(a):
+                                a = T.imm(-T.nodes[a][1])
+                            else:
+                                b = T.add_node(("N", b))   # lazy negation P - b (may equal P; fine inside a product)
+                        terms.append((a, b))
+                r = T.add_node(("d", tuple(terms)))
+            else:
+                ops = S.operands(cur)
+                pend = [x for x in ops if x not in memo]
+                if pend:
+                    stack.extend(pend)
+                    continue
+                if k[0] == "+":
+                    r = T.add(memo[k[1]], memo[k[2]])
+                elif k[0] == "-":
+                    r = T.sub(memo[k[1]], memo[k[2]])
+                elif k[0] == "n":
+                    r = T.neg(memo[k[1]])
+                elif k[0] == "*":
+                    r = T.mul(memo[k[1]], memo[k[2]])
+                elif k[0] == "d":
+                    r = T.add_node(("d", tuple((memo[a], memo[b]) for a, b in k[1])))
+                else:
+                    r = T.add_node(k)
+            memo[cur] = r
+            stack.pop()
+        return memo[root]
+
+    new_outs = [conv(o) for o in outs]
+    return T, new_outs
+
+
+def schedule_scalars(S, outs):
+    n = len(S.nodes)
+
+    def ops(i):
+        k = S.nodes[i]
+        if k[0] == "N":
+            return [k[1]]
+        return S.operands(i)
+
+    weight = [1] * n
+    for i in range(n):
+        w = 1
+        for o in ops(i):
+            w += weight[o]
+        weight[i] = min(w, 10**9)
+    order, seen = [], set()
+    for root in outs:
+        stack = [(root, False)]
+        while stack:
+            node, done = stack.pop()
+            if done:
+                order.append(node)
+                continue
+            if node in seen:
+                continue
+            seen.add(node)
+            stack.append((node, True))
+            for o in sorted(set(ops(node)), key=lambda x: weight[x]):   # heaviest pushed last -> visited first
+                stack.append((o, False))
+    return order
+
+
+# ------------------------------------------------------------------------------------------------ PTX emission
+class Ptx:
+    def __init__(self, S, name, lay):
+        self.S, self.name, self.lay = S, name, lay
+        self.body = []
+        self.nt = 0   # u32 temporaries
+        self.nw = 0   # u64 temporaries
+        self.bases = {}
+
+    def t(self):
+        self.nt += 1
+        return "%%t%d" % self.nt
+
+    def w(self):
+        self.nw += 1
+        return "%%w%d" % self.nw
+
+    def opnd(self, i):
+        k = self.S.nodes[i]
+        if k[0] == "i":
+            return str(k[1])
+        return "%%v%d" % i
+
+    def bound(self, i):
+        k = self.S.nodes[i]
+        if k[0] == "i":
+            return k[1]
+        if k[0] == "N":
+            return P
+        return P - 1
+
+    def emit(self, line):
+        self.body.append("    " + line)
+
+    def reduce_hi(self, acc, bound):
+        """bring a 64-bit accumulator (value <= bound) under P * 2^32; returns (acc', bound')"""
+        lim = P << 32
+        if bound < lim:
+            return acc, bound
+        lo, hi = self.t(), self.t()
+        self.emit("mov.b64 {%s, %s}, %s;" % (lo, hi, acc))
+        if bound >= 2 * lim:
+            h2, h3 = self.t(), self.t()
+            self.emit("add.u32 %s, %s, %d;" % (h2, hi, (1 << 32) - 2 * P))
+            self.emit("min.u32 %s, %s, %s;" % (h3, hi, h2))
+            hi = h3
+        h4, h5 = self.t(), self.t()
+        self.emit("add.u32 %s, %s, %d;" % (h4, hi, (1 << 32) - P))
+        self.emit("min.u32 %s, %s, %s;" % (h5, hi, h4))
+        acc2 = self.w()
+        self.emit("mov.b64 %s, {%s, %s};" % (acc2, lo, h5))
+        return acc2, lim - 1
+
+    def mont_finish(self, dst, acc):
+        lo, hi, m, hi2, x = self.t(), self.t(), self.t(), self.t(), self.t()
+        w2 = self.w()
+        self.emit("cvt.u32.u64 %s, %s;" % (lo, acc))
+        self.emit("mul.lo.u32 %s, %s, %d;" % (m, lo, NINV))
+        self.emit("mad.wide.u32 %s, %s, %d, %s;" % (w2, m, P, acc))
+        self.emit("mov.b64 {%s, %s}, %s;" % (x, hi2, w2))
+        hi3 = self.t()
+        self.emit("add.u32 %s, %s, %d;" % (hi3, hi2, (1 << 32) - P))
+        self.emit("min.u32 %s, %s, %s;" % (dst, hi2, hi3))
+
+    def node(self, i):
+        S = self.S
+        k = S.nodes[i]
+        o = k[0]
+        dst = "%%v%d" % i
+        if o == "i":
+            return
+        if o == "k":
+            self.emit("ld.param.u32 %s, [p_cst+%d];" % (dst, k[1]))
+        elif o == "t":
+            base = "%%b_%s_%d" % (k[1], k[3])
+            self.bases[(k[1], k[3])] = base
+            a = self.w()
+            self.emit("mad.wide.u32 %s, %%stride, %d, %s;" % (a, k[2], base))
+            self.emit("ld.global.nc.u32 %s, [%s];" % (dst, a))
+        elif o in "+-":
+            a, b = self.opnd(k[1]), self.opnd(k[2])
+            if S.nodes[k[1]][0] == "i":   # immediate first operand: materialise (only for '-', '+' is normalised)
+                m = self.t()
+                self.emit("mov.u32 %s, %s;" % (m, a))
+                a = m
+            t1, t2 = self.t(), self.t()
+            if o == "+":
+                self.emit("add.u32 %s, %s, %s;" % (t1, a, b))
+                self.emit("add.u32 %s, %s, %d;" % (t2, t1, (1 << 32) - P))
+            else:
+                self.emit("sub.u32 %s, %s, %s;" % (t1, a, b))
+                self.emit("add.u32 %s, %s, %d;" % (t2, t1, P))
+            self.emit("min.u32 %s, %s, %s;" % (dst, t1, t2))
+        elif o == "n":
+            t1, t2 = self.t(), self.t()
+            self.emit("neg.s32 %s, %s;" % (t1, self.opnd(k[1])))
+            self.emit("add.u32 %s, %s, %d;" % (t2, t1, P))
+            self.emit("min.u32 %s, %s, %s;" % (dst, t1, t2))
+        elif o == "N":
+            self.emit("sub.u32 %s, %d, %s;" % (dst, P, self.opnd(k[1])))
+        elif o == "*":
+            acc = self.w()
+            a, b = k[1], k[2]
+            if S.nodes[a][0] == "i":
+                a, b = b, a
+            self.emit("mul.wide.u32 %s, %s, %s;" % (acc, self.opnd(a), self.opnd(b)))
+            self.mont_finish(dst, acc)
+        elif o == "d":
+            acc, bound = None, 0
+            for a, b in k[1]:
+                if S.nodes[a][0] == "i":
+                    a, b = b, a
+                pb = self.bound(a) * self.bound(b)
+                if acc is not None and bound + pb >= (1 << 64):
+                    acc, bound = self.reduce_hi(acc, bound)
+                nacc = self.w()
+                if acc is None:
+                    self.emit("mul.wide.u32 %s, %s, %s;" % (nacc, self.opnd(a), self.opnd(b)))
+                else:
+                    self.emit("mad.wide.u32 %s, %s, %s, %s;" % (nacc, self.opnd(a), self.opnd(b), acc))
+                acc, bound = nacc, bound + pb
+            acc, bound = self.reduce_hi(acc, bound)
+            self.mont_finish(dst, acc)
+        else:
+            raise ValueError(k)
+
+    def kernel(self, order, outs, threads):
+        for i in order:
+            self.node(i)
+        nv = len(self.S.nodes)
+        L = []
+        L.append("// GENERATED by tools/gen_eval_check.py - do not edit.")
+        L.append(".version 8.6")
+        L.append(".target sm_100a")
+        L.append(".address_size 64")
+        L.append("")
+        L.append(".visible .entry %s(" % self.name)
+        L.append("    .param .u64 p_check, .param .u64 p_accum, .param .u64 p_data, .param .u32 p_domain, .param .u32 p_first,")
+        L.append("    .param .align 16 .b8 p_cst[%d])" % self.lay.size)
+        L.append(".maxntid %d, 1, 1" % threads)
+        L.append("{")
+        L.append("    .reg .pred %p<4>;")
+        L.append("    .reg .u32 %%v<%d>;" % (nv + 1))
+        L.append("    .reg .u32 %%t<%d>;" % (self.nt + 40))
+        L.append("    .reg .u64 %%w<%d>;" % (self.nw + 40))
+        L.append("    .reg .u32 %i, %domain, %mask, %first, %stride, %bdim, %bidx, %lane;")
+        L.append("    .reg .u32 %o<8>, %q<8>, %iy<6>, %res<4>;")
+        L.append("    .reg .u64 %check, %accum, %data, %oaddr<4>, %off;")
+        for (buf, back), base in sorted(self.bases.items()):
+            L.append("    .reg .u64 %s;" % base)
+        L.append("    ld.param.u64 %check, [p_check];")
+        L.append("    ld.param.u64 %accum, [p_accum];")
+        L.append("    ld.param.u64 %data, [p_data];")
+        L.append("    ld.param.u32 %domain, [p_domain];")
+        L.append("    ld.param.u32 %first, [p_first];")
+        L.append("    cvta.to.global.u64 %check, %check;")
+        L.append("    cvta.to.global.u64 %accum, %accum;")
+        L.append("    cvta.to.global.u64 %data, %data;")
+        L.append("    mov.u32 %bdim, %ntid.x;")
+        L.append("    mov.u32 %bidx, %ctaid.x;")
+        L.append("    mov.u32 %lane, %tid.x;")
+        L.append("    mad.lo.u32 %i, %bidx, %bdim, %lane;")
+        L.append("    setp.ge.u32 %p1, %i, %domain;")
+        L.append("    @%p1 bra DONE;")
+        L.append("    add.u32 %mask, %domain, -1;")
+        L.append("    shl.b32 %stride, %domain, 2;")
+        n = 0
+        for (buf, back), base in sorted(self.bases.items()):
+            # element index (i - 4*back) & mask, byte address = buf + 4 * index
+            L.append("    add.u32 %%q0, %%i, %d;" % ((-4 * back) % (1 << 32)))
+            L.append("    and.b32 %q0, %q0, %mask;")
+            L.append("    mad.wide.u32 %s, %%q0, 4, %%%s;" % (base, buf))
+            n += 1
+        L.extend(self.body)
+        # scale by inv_y[i & 3], accumulate into check unless this is the first part
+        L.append("    and.b32 %q1, %i, 3;")
+        L.append("    ld.param.u32 %%iy0, [p_cst+%d];" % self.lay.inv_y)
+        L.append("    ld.param.u32 %%iy1, [p_cst+%d];" % (self.lay.inv_y + 4))
+        L.append("    ld.param.u32 %%iy2, [p_cst+%d];" % (self.lay.inv_y + 8))
+        L.append("    ld.param.u32 %%iy3, [p_cst+%d];" % (self.lay.inv_y + 12))
+        L.append("    setp.eq.u32 %p2, %q1, 1;")
+        L.append("    selp.u32 %iy4, %iy1, %iy0, %p2;")
+        L.append("    setp.eq.u32 %p2, %q1, 2;")
+        L.append("    selp.u32 %iy4, %iy2, %iy4, %p2;")
+        L.append("    setp.eq.u32 %p2, %q1, 3;")
+        L.append("    selp.u32 %iy4, %iy3, %iy4, %p2;")
+        self.body = []
+        for c in range(4):
+            acc = self.w()
+            self.emit("mul.wide.u32 %s, %s, %%iy4;" % (acc, self.opnd(outs[c]) if self.S.nodes[outs[c]][0] != "i" else self._mat(outs[c])))
+            self.mont_finish("%%res%d" % c, acc)
+        L.extend(self.body)
+        L.append("    mul.wide.u32 %off, %i, 4;")
+        L.append("    add.u64 %oaddr0, %check, %off;")
+        L.append("    cvt.u64.u32 %off, %stride;")
+        L.append("    add.u64 %oaddr1, %oaddr0, %off;")
+        L.append("    add.u64 %oaddr2, %oaddr1, %off;")
+        L.append("    add.u64 %oaddr3, %oaddr2, %off;")
+        L.append("    setp.ne.u32 %p3, %first, 0;")
+        L.append("    @%p3 bra STORE;")
+        for c in range(4):
+            L.append("    ld.global.u32 %%o%d, [%%oaddr%d];" % (c, c))
+        for c in range(4):
+            L.append("    add.u32 %%q2, %%res%d, %%o%d;" % (c, c))
+            L.append("    add.u32 %%q3, %%q2, %d;" % ((1 << 32) - P))
+            L.append("    min.u32 %%res%d, %%q2, %%q3;" % c)
+        L.append("STORE:")
+        for c in range(4):
+            L.append("    st.global.u32 [%%oaddr%d], %%res%d;" % (c, c))
+        L.append("DONE:")
+        L.append("    ret;")
+        L.append("}")
+        return "\n".join(L) + "\n"
+
+    def _mat(self, i):
+        m = self.t()
+        self.emit("mov.u32 %s, %s;" % (m, self.S.nodes[i][1]))
+        return m
+
+
+LAUNCHER = r"""// GENERATED by tools/gen_eval_check.py - do not edit. Circuit %(name)s: host launcher of the %(nparts)d part kernels
+// (gen/eval_check_%(name)s_p*.ptx, assembled by ptxas and embedded in the library as cubins).
+//
+// Replaces CircuitHal::eval_check for %(name)s (risc0/zkp/src/hal/mod.rs:279-289; CPU spec
+// risc0/circuit/rv32im/src/prove/hal/cpu.rs:145-208; reference GPU path rv32im-sys/kernels/cuda/ffi_supra.cu:26-79).
+// The constraint polynomial is the sum of %(nparts)d groups of top-level terms; part j adds its group, already divided by
+// (3x)^N - 1, into `check` (part 0 stores). All per-proof constants travel in the kernel parameter block
+// (constant bank): poly_mix powers, their -11 multiples, globals, mix values and the 4 divisor inverses.
+#include <mutex>
+#include <vector>
+
+#include "../ctx.h"
+#include "../tables/circuit_%(name)s.h"
+#include "../tables/field_tables.h"
+
+using namespace r0;
+
+extern "C" {
+%(externs)s
+}
+
+namespace {
+struct Consts {
+  uint32_t pm[%(npm)d][4];
+  uint32_t npm[%(npm)d][4];
+  uint32_t global[%(n_global)d];
+  uint32_t mix[%(n_mix)d];
+  uint32_t inv_y[4];
+};
+static_assert(sizeof(Consts) == %(cst_size)d, "constant block layout differs from the generator's");
+
+constexpr int kParts = %(nparts)d;
+cudaKernel_t g_kernels[kParts];
+std::once_flag g_once;
+std::string g_load_error;
+
+void load_kernels() {
+  const void* images[kParts] = {%(images)s};
+  const char* names[kParts] = {%(names)s};
+  for (int j = 0; j < kParts; j++) {
+    cudaLibrary_t lib;
+    cudaError_t e = cudaLibraryLoadData(&lib, images[j], nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&g_kernels[j], lib, names[j]);
+    if (e != cudaSuccess) {
+      g_load_error = std::string("loading ") + names[j] + ": " + cudaGetErrorString(e);
+      return;
+    }
+  }
+}
+}  // namespace
+
+// check: 4 x domain words out. accum/data: evaluated groups (cols x domain), device. global_host: %(n_global)d words,
+// mix_host: %(n_mix)d words (host). poly_mix: the drawn FpExt. po2 = log2(cycles); domain = 4 << po2.
+void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, const uint32_t* data, const uint32_t* global_host,
+                         const uint32_t* mix_host, const FpExt& poly_mix, uint32_t po2) {
+  const size_t domain = size_t(4) << po2;
+  R0_CHECK(po2 + 2 <= 27 && domain <= 0x80000000ull, "eval_check: po2 out of range");
+  std::call_once(g_once, load_kernels);
+  if (!g_load_error.empty()) throw CudaError(g_load_error);
+  static thread_local Consts k;
+  // poly_mix^POLY_MIX_POWERS[k]: the table is increasing, so walk it with one running power
+  {
+    FpExt cur = ext_one();
+    uint32_t have = 0;
+    for (int j = 0; j < %(npm)d; j++) {
+      const uint32_t want = %(NAME)s_POLY_MIX_POWERS[j];
+      if (want < have) {
+        cur = ext_one();
+        have = 0;
+      }
+      if (want - have > 64) {
+        cur = ext_mul(cur, ext_pow(poly_mix, want - have));
+      } else {
+        for (uint32_t s = have; s < want; s++) cur = ext_mul(cur, poly_mix);
+      }
+      have = want;
+      for (int q = 0; q < 4; q++) {
+        k.pm[j][q] = cur.c[q];
+        k.npm[j][q] = fp_mul(cur.c[q], FP_NBETA);
+      }
+    }
+  }
+  memcpy(k.global, global_host, sizeof(k.global));
+  memcpy(k.mix, mix_host, sizeof(k.mix));
+  // (3 * w^i)^N - 1 with w = ROU_FWD[po2+2], N = 2^po2 depends only on i mod 4: (3^N) * w_4^(i mod 4) - 1
+  const uint32_t three_n = fp_pow(FP_THREE, uint64_t(1) << po2);
+  uint32_t cur = MONT_ONE;
+  for (int r = 0; r < 4; r++) {
+    k.inv_y[r] = fp_inv(fp_sub(fp_mul(three_n, cur), MONT_ONE));
+    cur = fp_mul(cur, R0_ROU_FWD_MONT[2]);
+  }
+  const unsigned threads = %(threads)d;
+  const unsigned blocks = (unsigned)((domain + threads - 1) / threads);
+  uint32_t domain32 = (uint32_t)domain;
+  for (int j = 0; j < kParts; j++) {
+    uint32_t first = j == 0 ? 1u : 0u;
+    void* args[] = {&check, &accum, &data, &domain32, &first, &k};
+    R0_CUDA(cudaLaunchKernel((const void*)g_kernels[j], dim3(blocks), dim3(threads), args, 0, c->stream));
+    count_launch(c);
+  }
+}
+"""
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "rv32im"
+    nparts, flatten, threads = 8, True, 128
+    for a in sys.argv:
+        if a.startswith("--parts="):
+            nparts = int(a.split("=")[1])
+        if a == "--no-flatten":
+            flatten = False
+    cfg = CIRCUITS[name]
+    ir_path = os.path.join(ROOT, "risc0_b200", "circuits", name + ".ir.json.gz")
+    if "--from-ir" in sys.argv or not os.path.exists(cfg["srcs"][0]):
+        dag = load_ir(ir_path)
+    else:
+        fns = ir.parse_functions(cfg["srcs"])
+        dag = ir.build_dag(fns, arg_names=cfg["arg_names"])
+        save_ir(dag, ir_path)
+    npm = 1 + max(k[1] for k in dag.nodes if k[0] == "pm")
+    lay = Layout(npm, cfg["n_global"], cfg["n_mix"])
+    uses = [0] * len(dag.nodes)
+    for k in dag.nodes:
+        if k[0] in "+-*":
+            uses[k[1]] += 1
+            uses[k[2]] += 1
+    parts = partition(dag, uses, nparts)
+    gen_dir = os.path.join(ROOT, "risc0_b200", "csrc", "gen")
+    os.makedirs(gen_dir, exist_ok=True)
+    for f in os.listdir(gen_dir):
+        if f.startswith("eval_check_%s" % name):
+            os.remove(os.path.join(gen_dir, f))
+    externs, images, names = [], [], []
+    for j, part in enumerate(parts):
+        S, outs = lower(dag, part["terms"], lay)
+        if flatten:
+            S, outs = flatten_sums(S, outs)
+        order = schedule_scalars(S, outs)
+        kname = "eval_check_%s_p%d" % (name, j)
+        ptx = Ptx(S, kname, lay).kernel(order, outs, threads)
+        with open(os.path.join(gen_dir, kname + ".ptx"), "w") as f:
+            f.write(ptx)
+        from collections import Counter
+        cnt = Counter(S.nodes[i][0] for i in order)
+        nprod = sum(len(S.nodes[i][1]) for i in order if S.nodes[i][0] == "d")
+        print("part %d: %d terms, scalar ops %s, dot products %d" % (j, len(part["terms"]), dict(cnt), nprod))
+        externs.append("extern const unsigned char r0_cubin_%s[];" % kname)
+        images.append("r0_cubin_%s" % kname)
+        names.append('"%s"' % kname)
+    params = dict(name=name, NAME=name.upper(), nparts=len(parts), npm=npm, n_global=cfg["n_global"], n_mix=cfg["n_mix"],
+                  cst_size=lay.size, threads=threads, externs="\n".join(externs), images=", ".join(images),
+                  names=", ".join(names))
+    with open(os.path.join(gen_dir, "eval_check_%s.cu" % name), "w") as f:
+        f.write(LAUNCHER % params)
+
+
+if __name__ == "__main__":
+    main()
