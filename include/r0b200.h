@@ -47,6 +47,11 @@ uint64_t r0b200_bytes_peak(r0b200_ctx* ctx);       /* MemoryTracker.peak analogu
 r0b200_err r0b200_timer_start(r0b200_ctx* ctx);
 r0b200_err r0b200_timer_stop(r0b200_ctx* ctx, float* ms);
 
+/* Per-op device timing (the reference's NVTX ranges / scope! timers, hal/cuda.rs + risc0_core::scope): begin clears
+ * and enables; end synchronises and writes JSON {"op": {"ms": device ms, "n": count, "bytes": algorithmic bytes}}. */
+r0b200_err r0b200_profile_begin(r0b200_ctx* ctx);
+r0b200_err r0b200_profile_end(r0b200_ctx* ctx, char* json_out, size_t cap);
+
 /* ---- buffers (Hal::alloc_* / copy_from_* hal/mod.rs:67-100; Buffer::view/get_at/view_mut hal/mod.rs:39-53) ---- */
 r0b200_err r0b200_alloc(r0b200_ctx* ctx, size_t bytes, void** dptr);
 r0b200_err r0b200_free(r0b200_ctx* ctx, void* dptr);

@@ -4,7 +4,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libr0b200.so")
+LIB_PATH = os.environ.get("R0B200_LIB") or os.path.join(HERE, "lib", "libr0b200.so")
 HEADER = os.path.join(HERE, "..", "include", "r0b200.h")
 
 

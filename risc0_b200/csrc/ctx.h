@@ -5,8 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "fp.cuh"
 
@@ -52,6 +54,39 @@ struct Ctx {
   size_t bytes_allocated = 0;  // MemoryTracker analogue (hal/mod.rs:292-317)
   size_t bytes_peak = 0;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  // optional per-phase device timing (r0b200_profile_begin / _end): event pairs recorded on `stream` around each op
+  bool profiling = false;
+  struct PhaseRec {
+    const char* name;
+    cudaEvent_t a, b;
+    double bytes;  // algorithmic bytes of the op (SURVEY 8d formulas), 0 if not stated
+  };
+  std::vector<PhaseRec> phase_log;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+// RAII phase marker used by the launchers; free when profiling is off.
+struct PhaseScope {
+  Ctx* c;
+  cudaEvent_t b = nullptr;
+  PhaseScope(Ctx* c_, const char* name, double bytes = 0) : c(c_) {
+    if (!c->profiling) return;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; i++) {
+      if (c->event_pool.empty()) {
+        cudaEventCreate(&ev[i]);
+      } else {
+        ev[i] = c->event_pool.back();
+        c->event_pool.pop_back();
+      }
+    }
+    cudaEventRecord(ev[0], c->stream);
+    b = ev[1];
+    c->phase_log.push_back({name, ev[0], ev[1], bytes});
+  }
+  ~PhaseScope() {
+    if (b) cudaEventRecord(b, c->stream);
+  }
 };
 
 inline void count_launch(Ctx* c, uint64_t n = 1) { c->launches += n; }

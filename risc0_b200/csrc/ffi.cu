@@ -42,6 +42,13 @@ void r0b200_destroy(r0b200_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   r0_ntt_free_tables(c);
+  for (auto& r : c->phase_log) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto& e : c->event_pool) cudaEventDestroy(e);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -77,6 +84,49 @@ r0b200_err r0b200_timer_stop(r0b200_ctx* ctx, float* ms) {
   R0_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
   R0_CUDA(cudaEventSynchronize(ctx->ev_stop));
   R0_CUDA(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+  R0_API_END
+}
+
+r0b200_err r0b200_profile_begin(r0b200_ctx* ctx) {
+  CTX_BEGIN
+  for (auto& r : ctx->phase_log) {
+    ctx->event_pool.push_back(r.a);
+    ctx->event_pool.push_back(r.b);
+  }
+  ctx->phase_log.clear();
+  ctx->profiling = true;
+  R0_API_END
+}
+// Writes a JSON object {"<phase>": {"ms": total device ms, "n": launches of the phase, "bytes": algorithmic bytes}, ...}
+r0b200_err r0b200_profile_end(r0b200_ctx* ctx, char* json_out, size_t cap) {
+  CTX_BEGIN
+  ctx->profiling = false;
+  R0_CUDA(cudaStreamSynchronize(ctx->stream));
+  struct Tot {
+    double ms = 0, bytes = 0;
+    size_t n = 0;
+  };
+  std::map<std::string, Tot> tot;
+  for (auto& r : ctx->phase_log) {
+    float ms = 0;
+    R0_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    Tot& t = tot[r.name];
+    t.ms += ms;
+    t.bytes += r.bytes;
+    t.n++;
+  }
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : tot) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"n\": %zu, \"bytes\": %.0f}", first ? "" : ", ", kv.first.c_str(),
+             kv.second.ms, kv.second.n, kv.second.bytes);
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  R0_CHECK(json_out != nullptr && js.size() + 1 <= cap, "profile_end: output buffer too small");
+  memcpy(json_out, js.c_str(), js.size() + 1);
   R0_API_END
 }
 

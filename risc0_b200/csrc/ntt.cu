@@ -386,6 +386,7 @@ static size_t auto_group(int k, size_t count, size_t bytes_per_elem_resident) {
 
 // io: count rows of 2^k, natural order in, bit-reversed coefficients out, scaled by 2^-k; zk: also * 3^brev(i)
 void r0_ntt_interpolate(Ctx* c, uint32_t* io, size_t count, int k, bool zk, size_t cols_per_launch) {
+  PhaseScope ph(c, zk ? "ntt_interpolate_zk" : "ntt_interpolate", 8.0 * (double)count * (double)(size_t(1) << k));
   R0_CHECK(k >= 0 && k <= MAX_LG, "batch_interpolate_ntt: size out of range");
   if (count == 0) return;
   NttArgs a{};
@@ -426,6 +427,7 @@ void r0_ntt_interpolate(Ctx* c, uint32_t* io, size_t count, int k, bool zk, size
 // out: count rows of 2^k ; in: count rows of 2^(k-eb), bit-reversed coefficient order; natural-order evaluations out
 void r0_ntt_expand_evaluate(Ctx* c, uint32_t* out, const uint32_t* in, size_t count, int k, int eb,
                             size_t cols_per_launch) {
+  PhaseScope ph(c, "ntt_expand_evaluate", (eb ? 5.0 : 8.0) * 4.0 * (double)count * (double)(size_t(1) << (k - eb)));
   R0_CHECK(k >= eb && k <= MAX_LG, "batch_expand_into_evaluate_ntt: size out of range");
   R0_CHECK(eb == 0 || eb == 2, "batch_expand_into_evaluate_ntt: expand_bits must be 0 or 2");
   if (count == 0) return;
@@ -461,6 +463,7 @@ void r0_ntt_expand_evaluate(Ctx* c, uint32_t* out, const uint32_t* in, size_t co
 }
 
 void r0_bit_reverse(Ctx* c, uint32_t* io, size_t count, int k) {
+  PhaseScope ph(c, "bit_reverse", 8.0 * (double)count * (double)(size_t(1) << k));
   R0_CHECK(k >= 0 && k <= 30, "batch_bit_reverse: size out of range");
   if (count == 0 || k < 2) return;
   int t = k / 2 < 5 ? k / 2 : 5;

@@ -318,6 +318,7 @@ using namespace r0;
 
 void r0_eltwise_add(Ctx* c, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) { LAUNCH_1D(k_add, n, out, a, b, n); }
 void r0_eltwise_copy(Ctx* c, uint32_t* out, const uint32_t* in, size_t n) {
+  PhaseScope ph(c, "eltwise_copy", 8.0 * (double)n);
   if ((n % 4) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)in % 16) == 0) {
     LAUNCH_1D(k_copy4, n / 4, (uint4*)out, (const uint4*)in, n / 4);
   } else {
@@ -325,8 +326,12 @@ void r0_eltwise_copy(Ctx* c, uint32_t* out, const uint32_t* in, size_t n) {
   }
 }
 void r0_eltwise_zeroize(Ctx* c, uint32_t* io, size_t n) { LAUNCH_1D(k_zeroize, n, io, n); }
-void r0_fill(Ctx* c, uint32_t* io, uint32_t v, size_t n) { LAUNCH_1D(k_fill, n, io, v, n); }
+void r0_fill(Ctx* c, uint32_t* io, uint32_t v, size_t n) {
+  PhaseScope ph(c, "fill", 4.0 * (double)n);
+  LAUNCH_1D(k_fill, n, io, v, n);
+}
 void r0_eltwise_sum_ext(Ctx* c, uint32_t* out, const uint32_t* in, size_t count, size_t to_add) {
+  PhaseScope ph(c, "eltwise_sum_extelem", 16.0 * (double)count * (double)(to_add + 1));
   LAUNCH_1D(k_sum_ext, count, out, (const uint4*)in, count, to_add);
 }
 void r0_zk_shift(Ctx* c, uint32_t* io, size_t count, int bits) {
@@ -351,6 +356,7 @@ struct Scratch {
 // passed to Scratch may be freed as soon as the constructor returns.
 
 void r0_fri_fold(Ctx* c, uint32_t* out, const uint32_t* in, size_t count, const FpExt& mix) {
+  PhaseScope ph(c, "fri_fold", 272.0 * (double)count);
   FpExt pows[16];
   FpExt cur = ext_one();
   for (int i = 0; i < 16; i++) {
@@ -367,6 +373,7 @@ void r0_fri_fold(Ctx* c, uint32_t* out, const uint32_t* in, size_t count, const 
 void r0_mix_poly_coeffs(Ctx* c, uint32_t* out, const FpExt& mix_start, const FpExt& mix, const uint32_t* in,
                         const uint32_t* combos_host, size_t input_size, size_t count) {
   if (input_size == 0 || count == 0) return;
+  PhaseScope ph(c, "mix_poly_coeffs", 4.0 * (double)input_size * (double)count);
   std::vector<FpExt> pows(input_size);
   FpExt cur = mix_start;
   for (size_t i = 0; i < input_size; i++) {
@@ -394,6 +401,7 @@ void r0_mix_poly_coeffs(Ctx* c, uint32_t* out, const FpExt& mix_start, const FpE
 
 void r0_batch_evaluate_any(Ctx* c, const uint32_t* coeffs, size_t n, const uint32_t* which_dev, const uint32_t* xs_dev,
                            uint32_t* out_dev, size_t eval_count) {
+  PhaseScope ph(c, "batch_evaluate_any", 4.0 * (double)n * (double)eval_count);
   if (eval_count == 0) return;
   const size_t per_block = (size_t)EV_T * EV_CH;
   const int nchunks = (int)((n + per_block - 1) / per_block);
@@ -444,6 +452,7 @@ void r0_prefix_products(Ctx* c, uint32_t* io, size_t n) {
 void r0_combos_prepare(Ctx* c, uint32_t* combos, const FpExt* coeff_u_host, size_t coeff_u_len, uint32_t combo_count,
                        size_t cycles, const uint32_t* reg_sizes, const uint32_t* reg_combo_ids, uint32_t nregs,
                        const FpExt& mix, uint32_t check_size) {
+  PhaseScope ph(c, "combos_prepare");
   std::vector<FpExt> pows(nregs + check_size);
   std::vector<uint32_t> pos(nregs);
   FpExt cur = ext_one();
@@ -474,6 +483,7 @@ void r0_combos_prepare(Ctx* c, uint32_t* combos, const FpExt* coeff_u_host, size
 
 // poly: n FpExt coefficients, divided in place by (x - z); the remainder is written to *remainder_dev.
 void r0_poly_divide(Ctx* c, uint32_t* poly, size_t n, const FpExt& z, uint32_t* remainder_dev) {
+  PhaseScope ph(c, "combos_divide", 32.0 * (double)n);
   if (n == 0) return;
   size_t nchunks = (n + DIV_L - 1) / DIV_L;
   Scratch h(c, nchunks * sizeof(FpExt));
@@ -489,6 +499,7 @@ void r0_poly_divide(Ctx* c, uint32_t* poly, size_t n, const FpExt& z, uint32_t* 
 
 // ---- batched query openings (product driver) ------------------------------------------------------------------
 void r0_gather_batched(Ctx* c, uint32_t* dst, const GatherJob* jobs_host, size_t njobs) {
+  PhaseScope ph(c, "gather");
   if (njobs == 0) return;
   Scratch d_jobs(c, jobs_host, njobs * sizeof(GatherJob));
   k_gather_batched<<<(unsigned)njobs, 128, 0, c->stream>>>(dst, d_jobs.as<GatherJob>());
@@ -496,6 +507,7 @@ void r0_gather_batched(Ctx* c, uint32_t* dst, const GatherJob* jobs_host, size_t
   R0_CUDA(cudaGetLastError());
 }
 void r0_gather_digests(Ctx* c, uint32_t* dst, const DigestJob* jobs_host, size_t njobs) {
+  PhaseScope ph(c, "gather");
   if (njobs == 0) return;
   Scratch d_jobs(c, jobs_host, njobs * sizeof(DigestJob));
   k_gather_digests<<<(unsigned)((njobs * 8 + 255) / 256), 256, 0, c->stream>>>(dst, d_jobs.as<DigestJob>(), njobs);

@@ -193,6 +193,7 @@ void r0_poseidon2_init(Ctx* c) {
 }
 
 void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
+  PhaseScope ph(c, "hash_rows", 4.0 * (double)rows * (double)cols + 32.0 * (double)rows);
   if (rows == 0) return;
   R0_CHECK(cols <= 0xffffffffull, "hash_rows: too many columns");
   p2_hash_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols);
@@ -201,6 +202,7 @@ void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows,
 }
 
 void r0_p2_hash_fold(Ctx* c, uint32_t* io, size_t in_size, size_t out_size) {
+  PhaseScope ph(c, "hash_fold", 96.0 * (double)out_size);
   R0_CHECK(in_size == 2 * out_size, "hash_fold: input_size must be 2 * output_size");
   if (out_size == 0) return;
   p2_hash_fold_kernel<<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(io, in_size, out_size);
@@ -210,6 +212,7 @@ void r0_p2_hash_fold(Ctx* c, uint32_t* io, size_t in_size, size_t out_size) {
 
 // All levels below `leaves` (a power of two): nodes[leaves .. 2*leaves) are the leaf digests, fills nodes[1 .. leaves).
 void r0_p2_merkle_fold_all(Ctx* c, uint32_t* nodes, size_t leaves) {
+  PhaseScope ph(c, "hash_fold", 96.0 * (double)(leaves - 1));
   size_t in_size = leaves;
   while (in_size > 1) {
     size_t out_size = in_size / 2;

@@ -85,12 +85,14 @@ __global__ void __launch_bounds__(256) sha_fold_kernel(uint32_t* io, size_t in_s
 using namespace r0;
 
 void r0_sha_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
+  PhaseScope ph(c, "hash_rows", 4.0 * (double)rows * (double)cols + 32.0 * (double)rows);
   if (rows == 0) return;
   sha_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols);
   count_launch(c);
   R0_CUDA(cudaGetLastError());
 }
 void r0_sha_hash_fold(Ctx* c, uint32_t* io, size_t in_size, size_t out_size) {
+  PhaseScope ph(c, "hash_fold", 96.0 * (double)out_size);
   R0_CHECK(in_size == 2 * out_size, "hash_fold: input_size must be 2 * output_size");
   if (out_size == 0) return;
   sha_fold_kernel<<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(io, in_size, out_size);

@@ -134,6 +134,19 @@ class B200Hal:
         check(self._l.r0b200_timer_stop(self._ctx, C.byref(ms)))
         return ms.value
 
+    def bytes_peak(self):
+        return int(self._l.r0b200_bytes_peak(self._ctx))
+
+    def profile_begin(self):
+        check(self._l.r0b200_profile_begin(self._ctx))
+
+    def profile_end(self):
+        """{op: {"ms": device ms, "n": launches, "bytes": algorithmic bytes}} since profile_begin"""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        check(self._l.r0b200_profile_end(self._ctx, buf, C.c_size_t(len(buf))))
+        return json.loads(buf.value.decode())
+
     # ---- allocation (hal/mod.rs:67-100)
     def alloc_elem(self, name, size):
         return Buffer(self, name, size, 1)

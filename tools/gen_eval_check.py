@@ -23,6 +23,8 @@ import json
 import os
 import sys
 
+sys.setrecursionlimit(200000)
+
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import circuit_ir as ir  # noqa: E402
 
@@ -418,7 +420,7 @@ def flatten_sums(S, outs):
                 need = []
                 for sg, x in lv:
                     kx = S.nodes[x]
-                    if uses[x] == 1 and kx[0] in "*d":
+                    if kx[0] == "*" or (uses[x] == 1 and kx[0] == "d"):
                         need.extend(S.operands(x))
                     else:
                         need.append(x)
@@ -429,7 +431,7 @@ def flatten_sums(S, outs):
                 terms = []
                 for sg, x in lv:
                     kx = S.nodes[x]
-                    if uses[x] == 1 and kx[0] == "*":
+                    if kx[0] == "*":      # a product costs one MAC wherever it is used: never worth a register
                         prods = [(memo[kx[1]], memo[kx[2]])]
                     elif uses[x] == 1 and kx[0] == "d":
                         prods = [(memo[a], memo[b]) for a, b in kx[1]]
@@ -511,6 +513,13 @@ class Ptx:
         self.body = []
         self.nt = 0   # u32 temporaries
         self.nw = 0   # u64 temporaries
+        self.nl = 0   # tap load registers
+        self.pos = 0
+        self.remat = int(os.environ.get("EVAL_REMAT_DIST", "400"))   # re-load / recompute instead of keeping alive
+        self.remat_cost = int(os.environ.get("EVAL_REMAT_COST", "8"))
+        self.split = int(os.environ.get("EVAL_SPLIT", "0"))
+        self.last_fence = 0
+        self.use_bar = os.environ.get("EVAL_BAR", "0") == "1"
         self.bases = {}
 
     def t(self):
@@ -537,6 +546,16 @@ class Ptx:
 
     def emit(self, line):
         self.body.append("    " + line)
+        self.pos += 1
+
+    def fence(self):
+        """basic-block boundary (a never-taken branch): keeps ptxas' scheduler from hoisting work across it, which is
+        what blows up register pressure on a 30k-instruction block"""
+        if self.split and self.pos - self.last_fence >= self.split:
+            # bar.sync also keeps the warps of a block within the same instruction-cache window: straight-line code
+            # is fetched once per block instead of once per warp
+            self.body.append("    bar.sync 0;" if self.use_bar else "    @%p0 bra DONE;")
+            self.last_fence = self.pos
 
     def reduce_hi(self, acc, bound):
         """bring a 64-bit accumulator (value <= bound) under P * 2^32; returns (acc', bound')"""
@@ -572,19 +591,13 @@ class Ptx:
         S = self.S
         k = S.nodes[i]
         o = k[0]
-        dst = "%%v%d" % i
+        dst = self.reg.get(i, "%%v%d" % i)
         if o == "i":
             return
         if o == "k":
             self.emit("ld.param.u32 %s, [p_cst+%d];" % (dst, k[1]))
-        elif o == "t":
-            base = "%%b_%s_%d" % (k[1], k[3])
-            self.bases[(k[1], k[3])] = base
-            a = self.w()
-            self.emit("mad.wide.u32 %s, %%stride, %d, %s;" % (a, k[2], base))
-            self.emit("ld.global.nc.u32 %s, [%s];" % (dst, a))
         elif o in "+-":
-            a, b = self.opnd(k[1]), self.opnd(k[2])
+            a, b = self.use(k[1]), self.use(k[2])
             if S.nodes[k[1]][0] == "i":   # immediate first operand: materialise (only for '-', '+' is normalised)
                 m = self.t()
                 self.emit("mov.u32 %s, %s;" % (m, a))
@@ -599,40 +612,150 @@ class Ptx:
             self.emit("min.u32 %s, %s, %s;" % (dst, t1, t2))
         elif o == "n":
             t1, t2 = self.t(), self.t()
-            self.emit("neg.s32 %s, %s;" % (t1, self.opnd(k[1])))
+            self.emit("neg.s32 %s, %s;" % (t1, self.use(k[1])))
             self.emit("add.u32 %s, %s, %d;" % (t2, t1, P))
             self.emit("min.u32 %s, %s, %s;" % (dst, t1, t2))
         elif o == "N":
-            self.emit("sub.u32 %s, %d, %s;" % (dst, P, self.opnd(k[1])))
+            self.emit("sub.u32 %s, %d, %s;" % (dst, P, self.use(k[1])))
         elif o == "*":
             acc = self.w()
             a, b = k[1], k[2]
             if S.nodes[a][0] == "i":
                 a, b = b, a
-            self.emit("mul.wide.u32 %s, %s, %s;" % (acc, self.opnd(a), self.opnd(b)))
-            self.mont_finish(dst, acc)
-        elif o == "d":
-            acc, bound = None, 0
-            for a, b in k[1]:
-                if S.nodes[a][0] == "i":
-                    a, b = b, a
-                pb = self.bound(a) * self.bound(b)
-                if acc is not None and bound + pb >= (1 << 64):
-                    acc, bound = self.reduce_hi(acc, bound)
-                nacc = self.w()
-                if acc is None:
-                    self.emit("mul.wide.u32 %s, %s, %s;" % (nacc, self.opnd(a), self.opnd(b)))
-                else:
-                    self.emit("mad.wide.u32 %s, %s, %s, %s;" % (nacc, self.opnd(a), self.opnd(b), acc))
-                acc, bound = nacc, bound + pb
-            acc, bound = self.reduce_hi(acc, bound)
+            self.emit("mul.wide.u32 %s, %s, %s;" % (acc, self.use(a), self.use(b)))
             self.mont_finish(dst, acc)
         else:
             raise ValueError(k)
 
-    def kernel(self, order, outs, threads):
-        for i in order:
+    # ---- demand-driven emission: a value is computed right before its first use; sums of products are streamed
+    # (operands of term j are computed, then multiplied into the running accumulators of every sibling sum that uses
+    # them) so that a long constraint sum never has more than one term's worth of temporaries alive.
+    def prepare(self):
+        S = self.S
+        n = len(S.nodes)
+        self.weight = [1] * n
+        for i in range(n):
+            w = 1
+            for o in self.ops(i):
+                w += self.weight[o]
+            self.weight[i] = min(w, 10**9)
+        self.done = set()
+        self.pos = 0
+        self.tap_state = {}
+        self.reg = {}        # node -> current register name
+        self.last_use = {}
+        self.ncopy = 0
+        # cost of recomputing a value from taps / constants (instructions), capped
+        self.cost = [0] * n
+        for i in range(n):
+            k = S.nodes[i]
+            if k[0] in "ik":
+                c = 0
+            elif k[0] == "t":
+                c = 2
+            else:
+                c = {"+": 3, "-": 3, "n": 3, "N": 1, "*": 6}.get(k[0], 0)
+                if k[0] == "d":
+                    c = 2 * len(k[1]) + 6
+                c += sum(self.cost[o] for o in set(self.ops(i)))
+            self.cost[i] = min(c, 10**6)
+        self.siblings = {}
+        for i, k in enumerate(S.nodes):
+            if k[0] == "d":
+                self.siblings.setdefault(self.signature(k), []).append(i)
+
+    def ops(self, i):
+        k = self.S.nodes[i]
+        if k[0] == "N":
+            return [k[1]]
+        return self.S.operands(i)
+
+    def is_const(self, i):
+        return self.S.nodes[i][0] in "ik"
+
+    def signature(self, k):
+        return tuple(sorted(set(x for ab in k[1] for x in ab if not self.is_const(x))))
+
+    def ensure(self, i):
+        if i in self.done:
+            return
+        S = self.S
+        k = S.nodes[i]
+        if k[0] == "d":
+            self.stream_dots([d for d in self.siblings[self.signature(k)] if d not in self.done])
+            return
+        if k[0] != "t":
+            for o in sorted(set(self.ops(i)), key=lambda x: -self.weight[x]):
+                self.ensure(o)
             self.node(i)
+            self.fence()
+        self.done.add(i)
+
+    def use(self, i):
+        """operand string for node i at the current position (taps are re-loaded when the last load is far behind)"""
+        k = self.S.nodes[i]
+        if k[0] == "i":
+            return str(k[1])
+        if k[0] == "t":
+            st = self.tap_state.get(i)
+            if st is None or self.pos - st[1] > self.remat:
+                reg = "%%l%d" % self.nl
+                self.nl += 1
+                base = "%%b_%s_%d" % (k[1], k[3])
+                self.bases[(k[1], k[3])] = base
+                a = self.w()
+                self.emit("mad.wide.u32 %s, %%stride, %d, %s;" % (a, k[2], base))
+                self.emit("ld.global.nc.u32 %s, [%s];" % (reg, a))
+                st = [reg, self.pos]
+                self.tap_state[i] = st
+            st[1] = self.pos
+            return st[0]
+        if k[0] != "k" and self.cost[i] <= self.remat_cost and self.pos - self.last_use.get(i, self.pos) > self.remat:
+            # cheap value whose previous use is far behind: recompute into a fresh register instead of keeping it alive
+            self.ncopy += 1
+            self.reg[i] = "%%c%d" % self.ncopy
+            self.node(i)
+        self.last_use[i] = self.pos
+        return self.reg.get(i, "%%v%d" % i)
+
+    def stream_dots(self, dots):
+        S = self.S
+        # align the siblings' terms by their non-constant operands
+        keyed = {}
+        for d in dots:
+            for a, b in S.nodes[d][1]:
+                if S.nodes[a][0] == "i":
+                    a, b = b, a
+                key = tuple(sorted(x for x in (a, b) if not self.is_const(x)))
+                keyed.setdefault(key, []).append((d, a, b))
+        acc = {d: None for d in dots}
+        bound = {d: 0 for d in dots}
+        order = sorted(keyed, key=lambda key: -max([self.weight[x] for x in key] or [0]))
+        for key in order:
+            for x in sorted(key, key=lambda x: -self.weight[x]):
+                self.ensure(x)
+            for d, a, b in keyed[key]:
+                for x in (a, b):
+                    self.ensure(x)      # constants: ld.param emitted on first use
+                pb = self.bound(a) * self.bound(b)
+                if acc[d] is not None and bound[d] + pb >= (1 << 64):
+                    acc[d], bound[d] = self.reduce_hi(acc[d], bound[d])
+                nacc = self.w()
+                if acc[d] is None:
+                    self.emit("mul.wide.u32 %s, %s, %s;" % (nacc, self.use(a), self.use(b)))
+                else:
+                    self.emit("mad.wide.u32 %s, %s, %s, %s;" % (nacc, self.use(a), self.use(b), acc[d]))
+                acc[d], bound[d] = nacc, bound[d] + pb
+        for d in dots:
+            a, bnd = self.reduce_hi(acc[d], bound[d])
+            self.mont_finish("%%v%d" % d, a)
+            self.done.add(d)
+        self.fence()
+
+    def kernel(self, order, outs, threads):
+        self.prepare()
+        for o in outs:
+            self.ensure(o)
         nv = len(self.S.nodes)
         L = []
         L.append("// GENERATED by tools/gen_eval_check.py - do not edit.")
@@ -644,10 +767,14 @@ class Ptx:
         L.append("    .param .u64 p_check, .param .u64 p_accum, .param .u64 p_data, .param .u32 p_domain, .param .u32 p_first,")
         L.append("    .param .align 16 .b8 p_cst[%d])" % self.lay.size)
         L.append(".maxntid %d, 1, 1" % threads)
+        if os.environ.get("EVAL_MAXNREG"):
+            L.append(".maxnreg %d" % int(os.environ["EVAL_MAXNREG"]))
         L.append("{")
         L.append("    .reg .pred %p<4>;")
         L.append("    .reg .u32 %%v<%d>;" % (nv + 1))
         L.append("    .reg .u32 %%t<%d>;" % (self.nt + 40))
+        L.append("    .reg .u32 %%l<%d>;" % (self.nl + 1))
+        L.append("    .reg .u32 %%c<%d>;" % (self.ncopy + 2))
         L.append("    .reg .u64 %%w<%d>;" % (self.nw + 40))
         L.append("    .reg .u32 %i, %domain, %mask, %first, %stride, %bdim, %bidx, %lane;")
         L.append("    .reg .u32 %o<8>, %q<8>, %iy<6>, %res<4>;")
@@ -670,6 +797,7 @@ class Ptx:
         L.append("    @%p1 bra DONE;")
         L.append("    add.u32 %mask, %domain, -1;")
         L.append("    shl.b32 %stride, %domain, 2;")
+        L.append("    setp.eq.u32 %p0, %domain, 3;")
         n = 0
         for (buf, back), base in sorted(self.bases.items()):
             # element index (i - 4*back) & mask, byte address = buf + 4 * index
@@ -693,7 +821,7 @@ class Ptx:
         self.body = []
         for c in range(4):
             acc = self.w()
-            self.emit("mul.wide.u32 %s, %s, %%iy4;" % (acc, self.opnd(outs[c]) if self.S.nodes[outs[c]][0] != "i" else self._mat(outs[c])))
+            self.emit("mul.wide.u32 %s, %s, %%iy4;" % (acc, self.use(outs[c]) if self.S.nodes[outs[c]][0] != "i" else self._mat(outs[c])))
             self.mont_finish("%%res%d" % c, acc)
         L.extend(self.body)
         L.append("    mul.wide.u32 %off, %i, 4;")
@@ -756,6 +884,7 @@ struct Consts {
 static_assert(sizeof(Consts) == %(cst_size)d, "constant block layout differs from the generator's");
 
 constexpr int kParts = %(nparts)d;
+const char* const kPartNames[kParts] = {%(part_names)s};
 cudaKernel_t g_kernels[kParts];
 std::once_flag g_once;
 std::string g_load_error;
@@ -783,6 +912,7 @@ void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, cons
   R0_CHECK(po2 + 2 <= 27 && domain <= 0x80000000ull, "eval_check: po2 out of range");
   std::call_once(g_once, load_kernels);
   if (!g_load_error.empty()) throw CudaError(g_load_error);
+  PhaseScope ph(c, "eval_check", (4.0 * %(ncols)d + 16.0) * (double)domain);
   static thread_local Consts k;
   // poly_mix^POLY_MIX_POWERS[k]: the table is increasing, so walk it with one running power
   {
@@ -821,6 +951,7 @@ void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, cons
   for (int j = 0; j < kParts; j++) {
     uint32_t first = j == 0 ? 1u : 0u;
     void* args[] = {&check, &accum, &data, &domain32, &first, &k};
+    PhaseScope part(c, kPartNames[j]);
     R0_CUDA(cudaLaunchKernel((const void*)g_kernels[j], dim3(blocks), dim3(threads), args, 0, c->stream));
     count_launch(c);
   }
@@ -830,7 +961,7 @@ void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, cons
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "rv32im"
-    nparts, flatten, threads = 8, True, 128
+    nparts, flatten, threads = int(os.environ.get("EVAL_PARTS", "8")), True, int(os.environ.get("EVAL_THREADS", "128"))
     for a in sys.argv:
         if a.startswith("--parts="):
             nparts = int(a.split("=")[1])
@@ -875,11 +1006,15 @@ def main():
         images.append("r0_cubin_%s" % kname)
         names.append('"%s"' % kname)
     params = dict(name=name, NAME=name.upper(), nparts=len(parts), npm=npm, n_global=cfg["n_global"], n_mix=cfg["n_mix"],
-                  cst_size=lay.size, threads=threads, externs="\n".join(externs), images=", ".join(images),
-                  names=", ".join(names))
+                  cst_size=lay.size, threads=threads, ncols=sum(cfg["cols"].values()), externs="\n".join(externs), images=", ".join(images),
+                  names=", ".join(names), part_names=", ".join('"eval_check_p%d"' % j for j in range(len(parts))))
     with open(os.path.join(gen_dir, "eval_check_%s.cu" % name), "w") as f:
         f.write(LAUNCHER % params)
 
 
 if __name__ == "__main__":
-    main()
+    import threading
+    threading.stack_size(1 << 29)   # the demand-driven emitter recurses along the DAG depth
+    t = threading.Thread(target=main)
+    t.start()
+    t.join()
