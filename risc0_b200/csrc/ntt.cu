@@ -74,93 +74,42 @@ __device__ __forceinline__ void radix_dit(uint32_t (&v)[1 << A]) {  // bit-rever
   }
 }
 
-// ---- one radix step of the in-shared-memory transform -------------------------------------------------------
-// Logical element (h, l), h < 2^m, l < T lives at s[pad16(h) * T + l].
-template <int A>
-__device__ __forceinline__ void step_dif(uint32_t* s, int m, int rem, int lgT, const uint32_t* __restrict__ tw_hi) {
-  const int T = 1 << lgT;
-  const int items = (1 << (m - A)) << lgT;
-  const int lgstride = rem - A;
-  for (int w = threadIdx.x; w < items; w += blockDim.x) {
-    const int l = w & (T - 1);
-    const int g = w >> lgT;
-    const int r = g & ((1 << lgstride) - 1);
-    const int base = ((g >> lgstride) << rem) + r;
-    uint32_t v[1 << A];
-#pragma unroll
-    for (int j = 0; j < (1 << A); ++j) v[j] = s[pad16(base + (j << lgstride)) * T + l];
-    radix_dif<A>(v);
-    if (lgstride > 0) {
-#pragma unroll
-      for (int j = 1; j < (1 << A); ++j) v[j] = fp_mul(v[j], tw_small(tw_hi, rem, (uint32_t)r * (__brev(j) >> (32 - A))));
-    }
-#pragma unroll
-    for (int j = 0; j < (1 << A); ++j) s[pad16(base + (j << lgstride)) * T + l] = v[j];
-  }
-}
-template <int A, int SKIP>
-__device__ __forceinline__ void step_dit(uint32_t* s, int m, int done, int lgT, const uint32_t* __restrict__ tw_hi) {
-  const int T = 1 << lgT;
-  const int items = (1 << (m - A)) << lgT;
-  for (int w = threadIdx.x; w < items; w += blockDim.x) {
-    const int l = w & (T - 1);
-    const int g = w >> lgT;
-    const int r = g & ((1 << done) - 1);
-    const int base = ((g >> done) << (done + A)) + r;
-    uint32_t v[1 << A];
-#pragma unroll
-    for (int j = 0; j < (1 << A); ++j) v[j] = s[pad16(base + (j << done)) * T + l];
-    if (done > 0) {
-#pragma unroll
-      for (int j = 1; j < (1 << A); ++j)
-        v[j] = fp_mul(v[j], tw_small(tw_hi, done + A, (uint32_t)r * (__brev(j) >> (32 - A))));
-    }
-    radix_dit<A, SKIP>(v);
-#pragma unroll
-    for (int j = 0; j < (1 << A); ++j) s[pad16(base + (j << done)) * T + l] = v[j];
-  }
-}
+// ---- register-resident radix steps ---------------------------------------------------------------------------
+// A tile is a 2^M-point transform over the row index h (x T adjacent columns l for the strided pass). It is computed
+// as a sequence of radix-2^A steps (A = 4 wherever possible); in each step a thread holds the 2^A elements
+// h = base + (j << S) in registers. Between two steps the elements are exchanged through shared memory, laid out as
+// s[pad(h) * T + l] with pad(h) = h + (h >> 4); because S is always 0, 4 or 8 the padded index is linear in j
+// (offset j * PSTRIDE), so every shared-memory address is base + immediate. The first step reads global memory
+// directly and the last one writes it directly (fused with the expand-by-4 load, the inter-pass twiddle, the 1/n scale
+// and the zk shift), so a 2^12-point tile makes only two trips through shared memory.
+__constant__ uint32_t c_p3top[MAX_LG + 1][16];  // [k][j] = 3^(brev4(j) << (k-4)) for k >= 4 (zk-shift epilogue)
 
-// natural in -> bit-reversed out (ROU_REV), no scaling. Caller syncs before (data loaded) ; ends synced.
-__device__ void sm_dif(uint32_t* s, int m, int lgT, const uint32_t* __restrict__ tw_hi) {
-  int rem = m;
-  while (rem > 0) {
-    const int a = rem < 4 ? rem : 4;
-    switch (a) {
-      case 4: step_dif<4>(s, m, rem, lgT, tw_hi); break;
-      case 3: step_dif<3>(s, m, rem, lgT, tw_hi); break;
-      case 2: step_dif<2>(s, m, rem, lgT, tw_hi); break;
-      default: step_dif<1>(s, m, rem, lgT, tw_hi); break;
-    }
-    rem -= a;
-    __syncthreads();
-  }
+__device__ __forceinline__ constexpr int brev_small(int j, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; ++b) r |= ((j >> b) & 1) << (bits - 1 - b);
+  return r;
 }
-// bit-reversed in -> natural out (ROU_FWD); the first `skip` (0 or 2) layers are skipped (replicated input).
-__device__ void sm_dit(uint32_t* s, int m, int lgT, int skip, const uint32_t* __restrict__ tw_hi) {
-  int done = 0;
-  const int tail = m & 3;  // steps from the bottom: 4,4,...,tail  (tail last unless m < 4)
-  while (done < m) {
-    const int a = (m - done >= 4) ? 4 : (m - done);
-    const bool first = done == 0;
-    if (first && skip == 2) {
-      switch (a) {
-        case 4: step_dit<4, 2>(s, m, done, lgT, tw_hi); break;
-        case 3: step_dit<3, 2>(s, m, done, lgT, tw_hi); break;
-        default: step_dit<2, 2>(s, m, done, lgT, tw_hi); break;
-      }
-    } else {
-      switch (a) {
-        case 4: step_dit<4, 0>(s, m, done, lgT, tw_hi); break;
-        case 3: step_dit<3, 0>(s, m, done, lgT, tw_hi); break;
-        case 2: step_dit<2, 0>(s, m, done, lgT, tw_hi); break;
-        default: step_dit<1, 0>(s, m, done, lgT, tw_hi); break;
-      }
-    }
-    done += a;
-    __syncthreads();
+__host__ __device__ constexpr int pstride(int s) { return s == 0 ? 1 : (s == 4 ? 17 : 272); }
+__device__ __forceinline__ int padh(int h) { return h + (h >> 4); }
+__host__ __device__ constexpr int pad_size(int m) { return (1 << m) + ((1 << m) >> 4) + 1; }
+
+// DIT: elements v[j] = x[base + (j << DONE)], r = base & (2^DONE - 1)
+template <int A, int DONE, int SKIP>
+__device__ __forceinline__ void dit_regs(uint32_t (&v)[1 << A], int r, const uint32_t* __restrict__ tw_hi) {
+  if (DONE > 0) {
+#pragma unroll
+    for (int j = 1; j < (1 << A); ++j) v[j] = fp_mul(v[j], __ldg(tw_hi + ((r * brev_small(j, A)) << (12 - DONE - A))));
   }
-  (void)tail;
+  radix_dit<A, SKIP>(v);
+}
+// DIF: elements v[j] = x[base + (j << LGS)], r = base & (2^LGS - 1)
+template <int A, int LGS>
+__device__ __forceinline__ void dif_regs(uint32_t (&v)[1 << A], int r, const uint32_t* __restrict__ tw_hi) {
+  radix_dif<A>(v);
+  if (LGS > 0) {
+#pragma unroll
+    for (int j = 1; j < (1 << A); ++j) v[j] = fp_mul(v[j], __ldg(tw_hi + ((r * brev_small(j, A)) << (12 - LGS - A))));
+  }
 }
 
 struct NttArgs {
@@ -171,92 +120,318 @@ struct NttArgs {
   int eb;        // expand bits (forward only): input rows have 2^(k-eb) elements
   int mode;      // inverse epilogue: 0 none, 1 * n^-1, 2 * n^-1 * 3^brev_k(i)
   uint32_t ninv;
+  size_t tiles_total;  // contiguous pass: number of 2^k2 tiles over all columns of this launch
   const uint32_t* tw_lo;
   const uint32_t* tw_hi;
   const uint32_t* p3_lo;
   const uint32_t* p3_hi_scaled;
 };
 
-// Contiguous pass. grid = (2^k1 tiles, columns).
-//  DIR 0: standalone 2^k2 DIF of in[col][tile*2^k2 ..] + scale epilogue.
-//  DIR 1: load 2^(k2-eb) inputs, replicate, standalone DIT with `eb` skipped layers; if k1 > 0 the inter-pass twiddle
-//         w_{2^k}^(brev_k1(tile) * i) is applied on store.
-template <int DIR>
-__global__ void __launch_bounds__(256) ntt_contig_kernel(NttArgs a) {
-  extern __shared__ uint32_t s[];
-  const int m = a.k2;
-  const int tile = blockIdx.x;
-  const size_t col = blockIdx.y;
-  const int n_tile = 1 << m;
-  uint32_t* out = a.out + (col << a.k) + ((size_t)tile << m);
-  if (DIR == 0) {
-    const uint32_t* in = a.in + (col << a.k) + ((size_t)tile << m);
-    for (int i = threadIdx.x; i < n_tile; i += blockDim.x) s[pad16(i)] = in[i];
-    __syncthreads();
-    sm_dif(s, m, 0, a.tw_hi);
-    for (int i = threadIdx.x; i < n_tile; i += blockDim.x) {
-      uint32_t v = s[pad16(i)];
-      if (a.mode == 1) {
-        v = fp_mul(v, a.ninv);
-      } else if (a.mode == 2) {
-        uint32_t p = ((uint32_t)tile << m) + i;
-        uint32_t e = __brev(p) >> (32 - a.k);
-        uint32_t sc = __ldg(a.p3_hi_scaled + (e >> 12));
-        uint32_t lo = e & 4095u;
-        if (lo) sc = fp_mul(sc, __ldg(a.p3_lo + lo));
-        v = fp_mul(v, sc);
+constexpr int NTT_THREADS = 256;
+
+// Geometry of one step inside a block that owns TILES tiles of 2^M rows x T columns.
+//   item index w -> (tile t, group g, column l); the thread's elements are rows base + (j << S), j < 2^A.
+template <int M, int A, int S, int LGT>
+struct StepGeom {
+  static constexpr int GROUPS = 1 << (M - A);          // per tile
+  static constexpr int ITEMS_PER_TILE = GROUPS << LGT;
+  __device__ static __forceinline__ void decode(int w, int& t, int& l, int& r, int& base) {
+    l = w & ((1 << LGT) - 1);
+    const int gg = w >> LGT;
+    t = gg >> (M - A);
+    const int g = gg & (GROUPS - 1);
+    r = g & ((1 << S) - 1);
+    base = ((g >> S) << (S + A)) + r;
+  }
+};
+
+// ---- contiguous pass -----------------------------------------------------------------------------------------
+// Block = BLOCK_ELEMS consecutive elements = TILES tiles of 2^M (M = k2). DIR 1 (forward): load 2^(M-EB) inputs per
+// tile (replicated 2^EB times), DIT with EB skipped layers, inter-pass twiddle on store when k1 > 0.
+// DIR 0 (inverse): DIF, then the scale / zk-shift epilogue.
+template <int M>
+struct ContigCfg {
+  static constexpr int BLOCK_LG = M > 12 ? M : 12;
+  static constexpr int TILES = 1 << (BLOCK_LG - M);
+  static constexpr int TILE_PAD = pad_size(M);
+  static constexpr size_t SMEM = (size_t)TILES * TILE_PAD * 4;
+};
+
+template <int M, int A, int DONE, int SKIP, int EB, bool FROM_GLOBAL, bool TO_GLOBAL>
+__device__ __forceinline__ void fwd_contig_step(const NttArgs& a, uint32_t* s, size_t tile0) {
+  using G = StepGeom<M, A, DONE, 0>;
+  constexpr int TILES = ContigCfg<M>::TILES;
+  constexpr int ITEMS = G::ITEMS_PER_TILE * TILES;
+  constexpr int PS = pstride(DONE);
+#pragma unroll 1
+  for (int w = threadIdx.x; w < ITEMS; w += NTT_THREADS) {
+    int t, l, r, base;
+    G::decode(w, t, l, r, base);
+    const size_t tile = tile0 + t;
+    if (tile >= a.tiles_total) continue;
+    uint32_t v[1 << A];
+    uint32_t* sp = s + t * ContigCfg<M>::TILE_PAD + padh(base);
+    if (FROM_GLOBAL) {
+      // DONE == 0: the thread's elements are 2^A consecutive outputs = 2^(A-EB) consecutive inputs
+      const uint32_t* in = a.in + (tile << (M - EB)) + (base >> EB);
+      if (A - EB == 2) {
+        const uint4 q = *reinterpret_cast<const uint4*>(in);
+        const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < (1 << A); ++j) v[j] = x[j >> EB];
+      } else if (A - EB == 4) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint4 q = reinterpret_cast<const uint4*>(in)[q4];
+          v[4 * q4] = q.x; v[4 * q4 + 1] = q.y; v[4 * q4 + 2] = q.z; v[4 * q4 + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < (1 << A); ++j) v[j] = in[j >> EB];
       }
-      out[i] = v;
+    } else {
+#pragma unroll
+      for (int j = 0; j < (1 << A); ++j) v[j] = sp[j * PS];
     }
-  } else {
-    const int n_in = n_tile >> a.eb;
-    const uint32_t* in = a.in + (col << (a.k - a.eb)) + ((size_t)tile << (m - a.eb));
-    for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
-      uint32_t v = in[i];
-      for (int r = 0; r < (1 << a.eb); ++r) s[pad16((i << a.eb) + r)] = v;
-    }
-    __syncthreads();
-    sm_dit(s, m, 0, a.eb, a.tw_hi);
-    const uint32_t bt = a.k1 ? (__brev((uint32_t)tile) >> (32 - a.k1)) : 0u;
-    for (int i = threadIdx.x; i < n_tile; i += blockDim.x) {
-      uint32_t v = s[pad16(i)];
-      if (a.k1 && bt && i) v = fp_mul(v, tw_big(a.tw_lo, a.tw_hi, a.k, bt * (uint32_t)i));
-      out[i] = v;
+    dit_regs<A, DONE, SKIP>(v, r, a.tw_hi);
+    if (TO_GLOBAL) {
+      uint32_t* out = a.out + (tile << M) + base;
+      if (a.k1) {
+        // inter-pass twiddle w_{2^k}^(brev_k1(column tile) * i), i = index inside the tile
+        const uint32_t bt = __brev((uint32_t)(tile & ((size_t(1) << a.k1) - 1))) >> (32 - a.k1);
+        if (bt) {
+#pragma unroll
+          for (int j = 0; j < (1 << A); ++j) {
+            const uint32_t i = (uint32_t)(base + (j << DONE));
+            if (i) v[j] = fp_mul(v[j], tw_big(a.tw_lo, a.tw_hi, a.k, bt * i));
+          }
+        }
+      }
+      if (DONE == 0 && A == 4) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          reinterpret_cast<uint4*>(out)[q4] = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < (1 << A); ++j) out[j << DONE] = v[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < (1 << A); ++j) sp[j * PS] = v[j];
     }
   }
 }
 
-// Strided pass (in place on a.out). grid = (2^k2 / T, columns); tile = 2^k1 rows x T adjacent columns.
-//  DIR 0: standalone 2^k1 DIF down the rows, then * w_{2^k}^(L * brev_k1(row)).
-//  DIR 1: standalone 2^k1 DIT down the rows (inputs were pre-twiddled by the contiguous pass).
-template <int DIR>
-__global__ void __launch_bounds__(256) ntt_strided_kernel(NttArgs a, int lgT) {
+template <int M, int EB>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_contig_kernel(NttArgs a) {
   extern __shared__ uint32_t s[];
-  const int T = 1 << lgT;
-  const int m = a.k1;
-  const size_t col = blockIdx.y;
-  const uint32_t L0 = blockIdx.x << lgT;
-  uint32_t* io = a.out + (col << a.k) + L0;
-  const int total = (1 << m) << lgT;
-  for (int w = threadIdx.x; w < total; w += blockDim.x) {
-    const int l = w & (T - 1), h = w >> lgT;
-    s[pad16(h) * T + l] = io[((size_t)h << a.k2) + l];
-  }
-  __syncthreads();
-  if (DIR == 0) {
-    sm_dif(s, m, lgT, a.tw_hi);
+  constexpr int Q = M / 4, REM = M % 4;
+  constexpr int TILES = ContigCfg<M>::TILES;
+  const size_t tile0 = (size_t)blockIdx.x * TILES;
+  if constexpr (Q == 0) {
+    fwd_contig_step<M, REM, 0, EB, EB, true, true>(a, s, tile0);   // M in 1..3 (M == 0 is handled by the host)
   } else {
-    sm_dit(s, m, lgT, 0, a.tw_hi);
-  }
-  for (int w = threadIdx.x; w < total; w += blockDim.x) {
-    const int l = w & (T - 1), h = w >> lgT;
-    uint32_t v = s[pad16(h) * T + l];
-    if (DIR == 0) {
-      const uint32_t L = L0 + l;
-      const uint32_t bh = __brev((uint32_t)h) >> (32 - m);
-      if (L && bh) v = fp_mul(v, tw_big(a.tw_lo, a.tw_hi, a.k, L * bh));
+    fwd_contig_step<M, 4, 0, EB, EB, true, (Q == 1 && REM == 0)>(a, s, tile0);
+    if constexpr (Q >= 2) {
+      __syncthreads();
+      fwd_contig_step<M, 4, 4, 0, EB, false, (Q == 2 && REM == 0)>(a, s, tile0);
     }
-    io[((size_t)h << a.k2) + l] = v;
+    if constexpr (Q >= 3) {
+      __syncthreads();
+      fwd_contig_step<M, 4, 8, 0, EB, false, (Q == 3 && REM == 0)>(a, s, tile0);
+    }
+    if constexpr (REM != 0) {
+      __syncthreads();
+      fwd_contig_step<M, REM, 4 * Q, 0, EB, false, true>(a, s, tile0);
+    }
+  }
+}
+
+template <int M, int A, int LGS, bool FROM_GLOBAL, bool TO_GLOBAL>
+__device__ __forceinline__ void inv_contig_step(const NttArgs& a, uint32_t* s, size_t tile0) {
+  using G = StepGeom<M, A, LGS, 0>;
+  constexpr int TILES = ContigCfg<M>::TILES;
+  constexpr int ITEMS = G::ITEMS_PER_TILE * TILES;
+  constexpr int PS = pstride(LGS);
+#pragma unroll 1
+  for (int w = threadIdx.x; w < ITEMS; w += NTT_THREADS) {
+    int t, l, r, base;
+    G::decode(w, t, l, r, base);
+    const size_t tile = tile0 + t;
+    if (tile >= a.tiles_total) continue;
+    uint32_t v[1 << A];
+    uint32_t* sp = s + t * ContigCfg<M>::TILE_PAD + padh(base);
+    if (FROM_GLOBAL) {
+      const uint32_t* in = a.in + (tile << M) + base;
+      if (LGS == 0 && A == 4) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint4 q = reinterpret_cast<const uint4*>(in)[q4];
+          v[4 * q4] = q.x; v[4 * q4 + 1] = q.y; v[4 * q4 + 2] = q.z; v[4 * q4 + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < (1 << A); ++j) v[j] = in[j << LGS];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < (1 << A); ++j) v[j] = sp[j * PS];
+    }
+    dif_regs<A, LGS>(v, r, a.tw_hi);
+    if (TO_GLOBAL) {
+      // LGS == 0: the thread owns 2^A consecutive outputs p = tile * 2^M + base + j
+      uint32_t* out = a.out + (tile << M) + base;
+      if (a.mode == 1) {
+#pragma unroll
+        for (int j = 0; j < (1 << A); ++j) v[j] = fp_mul(v[j], a.ninv);
+      } else if (a.mode == 2) {
+        // n^-1 * 3^brev_k(p); p = p0 + j with p0 a multiple of 2^A, so brev_k(p) = brev_k(p0) + (brev_A(j) << (k - A))
+        const uint32_t p0 = (uint32_t)(((tile << M) + base) & ((size_t(1) << a.k) - 1));
+        const uint32_t e0 = a.k ? (__brev(p0) >> (32 - a.k)) : 0u;
+        uint32_t sc = __ldg(a.p3_hi_scaled + (e0 >> 12));
+        const uint32_t lo = e0 & 4095u;
+        if (lo) sc = fp_mul(sc, __ldg(a.p3_lo + lo));
+#pragma unroll
+        for (int j = 0; j < (1 << A); ++j) {
+          // c_p3top[k][x] = 3^(brev4(x) << (k-4)); brev_A(j) << (k-A) == brev4(j << (4-A)) << (k-4)
+          const uint32_t f = (j == 0) ? sc : fp_mul(sc, c_p3top[a.k][j << (4 - A)]);
+          v[j] = fp_mul(v[j], f);
+        }
+      }
+      if (A == 4) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          reinterpret_cast<uint4*>(out)[q4] = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < (1 << A); ++j) out[j] = v[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < (1 << A); ++j) sp[j * PS] = v[j];
+    }
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_inv_contig_kernel(NttArgs a) {
+  extern __shared__ uint32_t s[];
+  constexpr int Q = M / 4, REM = M % 4;
+  constexpr int TILES = ContigCfg<M>::TILES;
+  const size_t tile0 = (size_t)blockIdx.x * TILES;
+  if constexpr (Q == 0) {
+    inv_contig_step<M, REM, 0, true, true>(a, s, tile0);
+  } else {
+    // remainder first (top layers), then radix-16 steps at strides 2^(4(Q-1)), ..., 16, 1
+    if constexpr (REM != 0) {
+      inv_contig_step<M, REM, 4 * Q, true, false>(a, s, tile0);
+      __syncthreads();
+    }
+    if constexpr (Q >= 3) {
+      inv_contig_step<M, 4, 8, (REM == 0), false>(a, s, tile0);
+      __syncthreads();
+    }
+    if constexpr (Q >= 2) {
+      inv_contig_step<M, 4, 4, (REM == 0 && Q == 2), false>(a, s, tile0);
+      __syncthreads();
+    }
+    inv_contig_step<M, 4, 0, (REM == 0 && Q == 1), true>(a, s, tile0);
+  }
+}
+
+// ---- strided pass (in place on a.out) ---------------------------------------------------------------------------
+// Block = 2^M rows (M = k1, row stride 2^k2) x T = 2^LGT adjacent columns. grid = (2^k2 / T, columns).
+//  DIR 0: standalone DIF down the rows, then * w_{2^k}^(L * brev_k1(row)) (L = column index inside the row).
+//  DIR 1: standalone DIT down the rows (inputs were pre-twiddled by the contiguous pass).
+template <int M>
+struct StridedCfg {
+  static constexpr int LGT = M <= 10 ? 4 : (M == 11 ? 3 : 2);
+  static constexpr size_t SMEM = ((size_t)pad_size(M) << LGT) * 4;
+};
+
+template <int M, int A, int S, int DIR, bool FROM_GLOBAL, bool TO_GLOBAL>
+__device__ __forceinline__ void strided_step(const NttArgs& a, uint32_t* s, uint32_t* io, uint32_t L0) {
+  constexpr int LGT = StridedCfg<M>::LGT;
+  constexpr int T = 1 << LGT;
+  using G = StepGeom<M, A, S, LGT>;
+  constexpr int ITEMS = G::ITEMS_PER_TILE;
+  constexpr int PS = pstride(S) * T;
+#pragma unroll 1
+  for (int w = threadIdx.x; w < ITEMS; w += NTT_THREADS) {
+    int t, l, r, base;
+    G::decode(w, t, l, r, base);
+    uint32_t v[1 << A];
+    uint32_t* sp = s + padh(base) * T + l;
+    uint32_t* gp = io + ((size_t)base << a.k2) + l;
+    if (FROM_GLOBAL) {
+#pragma unroll
+      for (int j = 0; j < (1 << A); ++j) v[j] = gp[(size_t)(j << S) << a.k2];
+    } else {
+#pragma unroll
+      for (int j = 0; j < (1 << A); ++j) v[j] = sp[j * PS];
+    }
+    if (DIR == 0) {
+      dif_regs<A, S>(v, r, a.tw_hi);
+    } else {
+      dit_regs<A, S, 0>(v, r, a.tw_hi);
+    }
+    if (TO_GLOBAL) {
+      if (DIR == 0) {
+        const uint32_t L = L0 + l;
+        if (L) {
+#pragma unroll
+          for (int j = 0; j < (1 << A); ++j) {
+            const uint32_t bh = __brev((uint32_t)(base + (j << S))) >> (32 - M);
+            if (bh) v[j] = fp_mul(v[j], tw_big(a.tw_lo, a.tw_hi, a.k, L * bh));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < (1 << A); ++j) gp[(size_t)(j << S) << a.k2] = v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < (1 << A); ++j) sp[j * PS] = v[j];
+    }
+  }
+}
+
+template <int M, int DIR>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_strided_kernel(NttArgs a) {
+  extern __shared__ uint32_t s[];
+  constexpr int Q = M / 4, REM = M % 4;
+  constexpr int LGT = StridedCfg<M>::LGT;
+  const uint32_t L0 = blockIdx.x << LGT;
+  uint32_t* io = a.out + ((size_t)blockIdx.y << a.k) + L0;
+  if constexpr (Q == 0) {
+    strided_step<M, REM, 0, DIR, true, true>(a, s, io, L0);
+  } else if constexpr (DIR == 1) {
+    strided_step<M, 4, 0, 1, true, (Q == 1 && REM == 0)>(a, s, io, L0);
+    if constexpr (Q >= 2) {
+      __syncthreads();
+      strided_step<M, 4, 4, 1, false, (Q == 2 && REM == 0)>(a, s, io, L0);
+    }
+    if constexpr (Q >= 3) {
+      __syncthreads();
+      strided_step<M, 4, 8, 1, false, (Q == 3 && REM == 0)>(a, s, io, L0);
+    }
+    if constexpr (REM != 0) {
+      __syncthreads();
+      strided_step<M, REM, 4 * Q, 1, false, true>(a, s, io, L0);
+    }
+  } else {
+    if constexpr (REM != 0) {
+      strided_step<M, REM, 4 * Q, 0, true, false>(a, s, io, L0);
+      __syncthreads();
+    }
+    if constexpr (Q >= 3) {
+      strided_step<M, 4, 8, 0, (REM == 0), false>(a, s, io, L0);
+      __syncthreads();
+    }
+    if constexpr (Q >= 2) {
+      strided_step<M, 4, 4, 0, (REM == 0 && Q == 2), false>(a, s, io, L0);
+      __syncthreads();
+    }
+    strided_step<M, 4, 0, 0, (REM == 0 && Q == 1), true>(a, s, io, L0);
   }
 }
 
@@ -329,6 +504,16 @@ void r0_ntt_init_tables(Ctx* c) {
     w16[1][j] = fp_pow(R0_ROU_FWD_MONT[4], j);
   }
   R0_CUDA(cudaMemcpyToSymbolAsync(c_w16, w16, sizeof(w16), 0, cudaMemcpyHostToDevice, c->stream));
+  // c_p3top[k][x] = 3^(brev4(x) * 2^(k-4)) (k >= 4) or 3^brev4(x) (k < 4, only x = j << (4-k) is used): zk-shift factors of the 16
+  // consecutive outputs a thread owns in the inverse transform's last step
+  static uint32_t p3top[MAX_LG + 1][16];
+  for (int k = 0; k <= MAX_LG; k++)
+    for (int x = 0; x < 16; x++) {
+      uint64_t b4 = brev_bits((uint32_t)x, 4);
+      uint64_t e = k >= 4 ? (b4 << (k - 4)) : b4;  // k < 4: x = j << (4-k), so brev4(x) = brev_k(j)
+      p3top[k][x] = fp_pow(FP_THREE, e);
+    }
+  R0_CUDA(cudaMemcpyToSymbolAsync(c_p3top, p3top, sizeof(p3top), 0, cudaMemcpyHostToDevice, c->stream));
   R0_CUDA(cudaStreamSynchronize(c->stream));
   R0_CUDA(cudaGetLastError());
   count_launch(c, 6);
@@ -365,30 +550,86 @@ static void split(int k, int& k1, int& k2) {
     k1 = k - k2;
   }
 }
-static int strided_lgT(int k1) { return k1 <= 11 ? 4 : 3; }
-static size_t contig_smem(int k2) { return ((size_t(1) << k2) + (size_t(1) << k2) / 16 + 1) * 4; }
-static size_t strided_smem(int k1, int lgT) { return (((size_t(1) << k1) + (size_t(1) << k1) / 16 + 1) << lgT) * 4; }
 
 template <typename K>
 static void set_smem(K kernel, size_t bytes) {
-  R0_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (bytes > 48 * 1024) R0_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
 // cols_per_launch: how many columns one pass-pair covers before moving on (keeps the two-pass intermediate of a
 // group inside L2). 0 = pick automatically from the working-set size.
 static size_t auto_group(int k, size_t count, size_t bytes_per_elem_resident) {
-  const size_t budget = 48u << 20;  // conservative share of the 126 MB L2
+  const size_t budget = 64u << 20;  // share of the 126 MB L2 left to the intermediate of one column group
   size_t per_col = (size_t(1) << k) * bytes_per_elem_resident;
   size_t g = budget / per_col;
   if (g < 1) g = 1;
   return g > count ? count : g;
 }
 
+#define R0_FOR_M(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+
+template <int M>
+static void launch_inv_contig(Ctx* c, const NttArgs& a) {
+  constexpr int TILES = ContigCfg<M>::TILES;
+  set_smem(ntt_inv_contig_kernel<M>, ContigCfg<M>::SMEM);
+  const size_t blocks = (a.tiles_total + TILES - 1) / TILES;
+  ntt_inv_contig_kernel<M><<<(unsigned)blocks, NTT_THREADS, ContigCfg<M>::SMEM, c->stream>>>(a);
+}
+template <int M>
+static void launch_fwd_contig(Ctx* c, const NttArgs& a) {
+  constexpr int TILES = ContigCfg<M>::TILES;
+  const size_t blocks = (a.tiles_total + TILES - 1) / TILES;
+  if (a.eb == 2) {
+    if constexpr (M >= 2) {
+      set_smem(ntt_fwd_contig_kernel<M, 2>, ContigCfg<M>::SMEM);
+      ntt_fwd_contig_kernel<M, 2><<<(unsigned)blocks, NTT_THREADS, ContigCfg<M>::SMEM, c->stream>>>(a);
+    }
+  } else {
+    set_smem(ntt_fwd_contig_kernel<M, 0>, ContigCfg<M>::SMEM);
+    ntt_fwd_contig_kernel<M, 0><<<(unsigned)blocks, NTT_THREADS, ContigCfg<M>::SMEM, c->stream>>>(a);
+  }
+}
+template <int M, int DIR>
+static void launch_strided(Ctx* c, const NttArgs& a, size_t ncols) {
+  set_smem(ntt_strided_kernel<M, DIR>, StridedCfg<M>::SMEM);
+  dim3 grid(1u << (a.k2 - StridedCfg<M>::LGT), (unsigned)ncols);
+  ntt_strided_kernel<M, DIR><<<grid, NTT_THREADS, StridedCfg<M>::SMEM, c->stream>>>(a);
+}
+
+static void dispatch_inv_contig(Ctx* c, const NttArgs& a) {
+  switch (a.k2) {
+#define X(M) case M: launch_inv_contig<M>(c, a); break;
+    R0_FOR_M(X)
+#undef X
+    default: throw std::invalid_argument("ntt: unsupported tile size");
+  }
+  count_launch(c);
+}
+static void dispatch_fwd_contig(Ctx* c, const NttArgs& a) {
+  switch (a.k2) {
+#define X(M) case M: launch_fwd_contig<M>(c, a); break;
+    R0_FOR_M(X)
+#undef X
+    default: throw std::invalid_argument("ntt: unsupported tile size");
+  }
+  count_launch(c);
+}
+template <int DIR>
+static void dispatch_strided(Ctx* c, const NttArgs& a, size_t ncols) {
+  switch (a.k1) {
+#define X(M) case M: launch_strided<M, DIR>(c, a, ncols); break;
+    R0_FOR_M(X)
+#undef X
+    default: throw std::invalid_argument("ntt: unsupported tile size");
+  }
+  count_launch(c);
+}
+
 // io: count rows of 2^k, natural order in, bit-reversed coefficients out, scaled by 2^-k; zk: also * 3^brev(i)
 void r0_ntt_interpolate(Ctx* c, uint32_t* io, size_t count, int k, bool zk, size_t cols_per_launch) {
-  PhaseScope ph(c, zk ? "ntt_interpolate_zk" : "ntt_interpolate", 8.0 * (double)count * (double)(size_t(1) << k));
   R0_CHECK(k >= 0 && k <= MAX_LG, "batch_interpolate_ntt: size out of range");
-  if (count == 0) return;
+  PhaseScope ph(c, zk ? "ntt_interpolate_zk" : "ntt_interpolate", 8.0 * (double)count * (double)(size_t(1) << k));
+  if (count == 0 || k == 0) return;  // a 1-point transform is the identity (n^-1 = 3^0 = 1)
   NttArgs a{};
   a.k = k;
   split(k, a.k1, a.k2);
@@ -399,27 +640,15 @@ void r0_ntt_interpolate(Ctx* c, uint32_t* io, size_t count, int k, bool zk, size
   a.tw_hi = c->tab.tw_hi[0];
   a.p3_lo = c->tab.p3_lo;
   a.p3_hi_scaled = zk ? scaled_p3(c, k) : nullptr;
-  const size_t sm2 = contig_smem(a.k2);
-  set_smem(ntt_contig_kernel<0>, sm2);
   size_t group = cols_per_launch ? cols_per_launch : (a.k1 ? auto_group(k, count, 4) : count);
   if (group > 65535) group = 65535;
-  int lgT = 0;
-  size_t sm1 = 0;
-  if (a.k1) {
-    lgT = strided_lgT(a.k1);
-    sm1 = strided_smem(a.k1, lgT);
-    set_smem(ntt_strided_kernel<0>, sm1);
-  }
   for (size_t c0 = 0; c0 < count; c0 += group) {
     size_t nc = count - c0 < group ? count - c0 : group;
     a.in = io + (c0 << k);
     a.out = io + (c0 << k);
-    if (a.k1) {
-      ntt_strided_kernel<0><<<dim3(1u << (a.k2 - lgT), (unsigned)nc), 256, sm1, c->stream>>>(a, lgT);
-      count_launch(c);
-    }
-    ntt_contig_kernel<0><<<dim3(1u << a.k1, (unsigned)nc), 256, sm2, c->stream>>>(a);
-    count_launch(c);
+    a.tiles_total = nc << a.k1;
+    if (a.k1) dispatch_strided<0>(c, a, nc);
+    dispatch_inv_contig(c, a);
   }
   R0_CUDA(cudaGetLastError());
 }
@@ -427,37 +656,29 @@ void r0_ntt_interpolate(Ctx* c, uint32_t* io, size_t count, int k, bool zk, size
 // out: count rows of 2^k ; in: count rows of 2^(k-eb), bit-reversed coefficient order; natural-order evaluations out
 void r0_ntt_expand_evaluate(Ctx* c, uint32_t* out, const uint32_t* in, size_t count, int k, int eb,
                             size_t cols_per_launch) {
-  PhaseScope ph(c, "ntt_expand_evaluate", (eb ? 5.0 : 8.0) * 4.0 * (double)count * (double)(size_t(1) << (k - eb)));
   R0_CHECK(k >= eb && k <= MAX_LG, "batch_expand_into_evaluate_ntt: size out of range");
   R0_CHECK(eb == 0 || eb == 2, "batch_expand_into_evaluate_ntt: expand_bits must be 0 or 2");
+  PhaseScope ph(c, "ntt_expand_evaluate", (eb ? 5.0 : 8.0) * 4.0 * (double)count * (double)(size_t(1) << (k - eb)));
   if (count == 0) return;
+  if (k == 0) {
+    R0_CUDA(cudaMemcpyAsync(out, in, count * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return;
+  }
   NttArgs a{};
   a.k = k;
   split(k, a.k1, a.k2);
   a.eb = eb;
   a.tw_lo = c->tab.tw_lo[1];
   a.tw_hi = c->tab.tw_hi[1];
-  const size_t sm2 = contig_smem(a.k2);
-  set_smem(ntt_contig_kernel<1>, sm2);
   size_t group = cols_per_launch ? cols_per_launch : (a.k1 ? auto_group(k, count, 4) : count);
   if (group > 65535) group = 65535;
-  int lgT = 0;
-  size_t sm1 = 0;
-  if (a.k1) {
-    lgT = strided_lgT(a.k1);
-    sm1 = strided_smem(a.k1, lgT);
-    set_smem(ntt_strided_kernel<1>, sm1);
-  }
   for (size_t c0 = 0; c0 < count; c0 += group) {
     size_t nc = count - c0 < group ? count - c0 : group;
     a.in = in + (c0 << (k - eb));
     a.out = out + (c0 << k);
-    ntt_contig_kernel<1><<<dim3(1u << a.k1, (unsigned)nc), 256, sm2, c->stream>>>(a);
-    count_launch(c);
-    if (a.k1) {
-      ntt_strided_kernel<1><<<dim3(1u << (a.k2 - lgT), (unsigned)nc), 256, sm1, c->stream>>>(a, lgT);
-      count_launch(c);
-    }
+    a.tiles_total = nc << a.k1;
+    dispatch_fwd_contig(c, a);
+    if (a.k1) dispatch_strided<1>(c, a, nc);
   }
   R0_CUDA(cudaGetLastError());
 }
