@@ -39,39 +39,48 @@ __device__ __forceinline__ uint32_t tw_big(const uint32_t* __restrict__ lo, cons
 }
 
 // ---- in-register radix-2^A transforms with compile-time twiddles --------------------------------------------
+// Every loop bound is a template constant so the butterflies unroll completely and v[] stays in registers.
+template <int A, int S>
+__device__ __forceinline__ void dif_layer(uint32_t (&v)[1 << A]) {
+  constexpr int half = 1 << (S - 1);
+#pragma unroll
+  for (int b = 0; b < (1 << A); b += 2 * half) {
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const uint32_t x = v[b + i], y = v[b + i + half];
+      v[b + i] = fp_add(x, y);
+      const uint32_t d = fp_sub(x, y);
+      v[b + i + half] = (i == 0) ? d : fp_mul(d, c_w16[0][i << (4 - S)]);
+    }
+  }
+}
 template <int A>
 __device__ __forceinline__ void radix_dif(uint32_t (&v)[1 << A]) {  // natural in, bit-reversed out, ROU_REV
+  if constexpr (A >= 4) dif_layer<A, 4>(v);
+  if constexpr (A >= 3) dif_layer<A, 3>(v);
+  if constexpr (A >= 2) dif_layer<A, 2>(v);
+  if constexpr (A >= 1) dif_layer<A, 1>(v);
+}
+template <int A, int S>
+__device__ __forceinline__ void dit_layer(uint32_t (&v)[1 << A]) {
+  constexpr int half = 1 << (S - 1);
 #pragma unroll
-  for (int s = A; s >= 1; --s) {
-    const int half = 1 << (s - 1);
+  for (int b = 0; b < (1 << A); b += 2 * half) {
 #pragma unroll
-    for (int b = 0; b < (1 << A); b += 2 * half) {
-#pragma unroll
-      for (int i = 0; i < half; ++i) {
-        uint32_t x = v[b + i], y = v[b + i + half];
-        v[b + i] = fp_add(x, y);
-        uint32_t d = fp_sub(x, y);
-        v[b + i + half] = (i == 0) ? d : fp_mul(d, c_w16[0][i << (4 - s)]);
-      }
+    for (int i = 0; i < half; ++i) {
+      const uint32_t x = v[b + i];
+      const uint32_t y = (i == 0) ? v[b + i + half] : fp_mul(v[b + i + half], c_w16[1][i << (4 - S)]);
+      v[b + i] = fp_add(x, y);
+      v[b + i + half] = fp_sub(x, y);
     }
   }
 }
 template <int A, int SKIP>
 __device__ __forceinline__ void radix_dit(uint32_t (&v)[1 << A]) {  // bit-reversed in, natural out, ROU_FWD
-#pragma unroll
-  for (int s = SKIP + 1; s <= A; ++s) {
-    const int half = 1 << (s - 1);
-#pragma unroll
-    for (int b = 0; b < (1 << A); b += 2 * half) {
-#pragma unroll
-      for (int i = 0; i < half; ++i) {
-        uint32_t x = v[b + i];
-        uint32_t y = (i == 0) ? v[b + i + half] : fp_mul(v[b + i + half], c_w16[1][i << (4 - s)]);
-        v[b + i] = fp_add(x, y);
-        v[b + i + half] = fp_sub(x, y);
-      }
-    }
-  }
+  if constexpr (A >= 1 && SKIP < 1) dit_layer<A, 1>(v);
+  if constexpr (A >= 2 && SKIP < 2) dit_layer<A, 2>(v);
+  if constexpr (A >= 3 && SKIP < 3) dit_layer<A, 3>(v);
+  if constexpr (A >= 4 && SKIP < 4) dit_layer<A, 4>(v);
 }
 
 // ---- register-resident radix steps ---------------------------------------------------------------------------
