@@ -227,66 +227,124 @@ __global__ void k_combos_prepare(FpExt* combos, const FpExt* coeff_u, uint32_t c
   }
 }
 
-// ---- combos_divide: in-place synthetic division by (x - z) as a three-kernel chunked Horner scan ---------------
-// q[i] = sum_{j > i} p[j] z^(j-i-1). Chunk c covers [c*L, (c+1)*L). Phase 1: h_c = sum_{j in c} p[j] z^(j - c*L).
-// Phase 2 (one block): carry_c = sum_{c' > c} h_c' z^((c'-c-1) L)  (the value "cur" has when entering chunk c from above).
-// Phase 3: serial Horner inside the chunk seeded with carry_c. Remainder = value after index 0.
-constexpr int DIV_L = 64;  // coefficients per thread
+// ---- combos_divide: in-place synthetic division by (x - z) as a blocked suffix scan ------------------------------
+// q[i] = sum_{j > i} p[j] z^(j-i-1), remainder = sum_j p[j] z^j. A block owns DIV_SEG = 256 x 8 consecutive
+// coefficients (one 128-byte line per thread). Phase A: local Horner per thread, tree-combined to the block's value
+// H_b = sum_j p[b*SEG + j] z^j. Phase B (one block): carry into block b = sum_{b' > b} H_b' Z^(b'-b-1), Z = z^SEG,
+// as a Kogge-Stone suffix scan. Phase C: recompute the local values, scan them inside the block, add the block carry
+// and run the Horner recurrence again, this time writing the quotient. Powers of z come from a small table built on
+// the host (DivPowers), so the kernels contain no exponentiation.
+constexpr int DIV_E = 8;                 // coefficients per thread
+constexpr int DIV_B = 256;               // threads per block
+constexpr int DIV_SEG = DIV_E * DIV_B;   // coefficients per block
+constexpr int DIV_MAXLG = 14;            // up to 2^14 blocks = 2^25 coefficients
 
-__global__ void k_div_phase1(FpExt* h, const FpExt* p, size_t n, FpExt z) {
-  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t nchunks = (n + DIV_L - 1) / DIV_L;
-  if (c >= nchunks) return;
-  size_t lo = c * DIV_L, hi = lo + DIV_L < n ? lo + DIV_L : n;
-  FpExt acc = ext_zero();
-  for (size_t j = hi; j-- > lo;) acc = ext_add(ext_mul(acc, z), p[j]);
-  h[c] = acc;
+struct DivPowers {
+  FpExt z;                  // z
+  FpExt zs[8];              // z^(8 * 2^s): in-block scan strides
+  FpExt zt[DIV_B];          // z^(8 * (255 - t)): weight of the block carry for thread t
+  FpExt Z[DIV_MAXLG + 1];   // (z^SEG)^(2^s): cross-block scan strides
+};
+
+__device__ __forceinline__ FpExt ld_ext(const FpExt* p) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  return FpExt{{q.x, q.y, q.z, q.w}};
 }
-// single block; zL = z^DIV_L. carry[c] computed by a serial sweep from the top (nchunks <= 2^18 for n = 2^24;
-// split into 256 threads by a two-level scheme: each thread owns a contiguous run of chunks)
-__global__ void k_div_phase2(FpExt* carry, const FpExt* h, size_t nchunks, FpExt zL) {
-  __shared__ FpExt run_sum[256];   // Horner value of the thread's run (relative to the run start)
-  __shared__ FpExt run_carry[256];
-  const int t = threadIdx.x, T = blockDim.x;
-  const size_t per = (nchunks + T - 1) / T;
-  const size_t lo = (size_t)t * per, hi = lo + per < nchunks ? lo + per : nchunks;
-  FpExt acc = ext_zero();
-  for (size_t c = hi; c-- > lo && hi > lo;) acc = ext_add(ext_mul(acc, zL), h[c]);
-  run_sum[t] = acc;
+__device__ __forceinline__ void st_ext(FpExt* p, const FpExt& v) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(v.c[0], v.c[1], v.c[2], v.c[3]);
+}
+
+// loads the thread's 8 coefficients (zero beyond n) and returns their local Horner value sum_j c[j] z^j
+__device__ __forceinline__ FpExt div_local(const FpExt* p, size_t n, size_t lo, const FpExt& z, FpExt (&c)[DIV_E]) {
+#pragma unroll
+  for (int j = 0; j < DIV_E; j++) c[j] = (lo + j < n) ? ld_ext(p + lo + j) : ext_zero();
+  FpExt acc = c[DIV_E - 1];
+#pragma unroll
+  for (int j = DIV_E - 2; j >= 0; j--) acc = ext_add(ext_mul(acc, z), c[j]);
+  return acc;
+}
+
+__global__ void __launch_bounds__(DIV_B) k_div_block_totals(FpExt* totals, const FpExt* p, size_t n, const DivPowers* pw) {
+  __shared__ FpExt sh[DIV_B];
+  const int t = threadIdx.x;
+  const size_t lo = ((size_t)blockIdx.x * DIV_B + t) * DIV_E;
+  FpExt c[DIV_E];
+  sh[t] = div_local(p, n, lo, pw->z, c);
   __syncthreads();
-  if (t == 0) {
-    const FpExt zrun = ext_pow(zL, per);
-    FpExt cur = ext_zero();
-    for (int r = T - 1; r >= 0; r--) {
-      run_carry[r] = cur;  // value entering run r from above, at chunk granularity
-      cur = ext_add(ext_mul(cur, zrun), run_sum[r]);
-      // note: a short last run (hi - lo < per) still uses zrun: its missing high chunks are zeros, exact.
-    }
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const int d = 1 << s;
+    if ((t & (2 * d - 1)) == 0) sh[t] = ext_add(sh[t], ext_mul(pw->zs[s], sh[t + d]));
+    __syncthreads();
   }
-  __syncthreads();
-  FpExt cur = run_carry[t];
-  // entering the top chunk of this run: account for chunks missing at the top of a short run
-  if (hi > lo) {
-    size_t missing = per - (hi - lo);
-    if (missing) cur = ext_mul(cur, ext_pow(zL, missing));
-    for (size_t c = hi; c-- > lo;) {
-      carry[c] = cur;
-      cur = ext_add(ext_mul(cur, zL), h[c]);
+  if (t == 0) totals[blockIdx.x] = sh[0];
+}
+
+// carry[b] = sum_{b' > b} totals[b'] Z^(b'-b-1); one block, processes the blocks in windows of 1024 from the top
+__global__ void __launch_bounds__(1024) k_div_block_carries(FpExt* carry, const FpExt* totals, size_t nblocks,
+                                                            const DivPowers* pw) {
+  __shared__ FpExt sh[2][1024];
+  __shared__ FpExt above;  // carry entering the current window from the blocks above it
+  const int t = threadIdx.x;
+  if (t == 0) above = ext_zero();
+  const size_t nwin = (nblocks + 1023) / 1024;
+  for (size_t wi = nwin; wi-- > 0;) {
+    const size_t b = wi * 1024 + t;
+    // inclusive suffix scan S_t = sum_{t' >= t} H_t' Z^(t'-t) inside the window
+    int cur = 0;
+    sh[0][t] = b < nblocks ? totals[b] : ext_zero();
+    __syncthreads();
+    for (int s = 0; s < 10; s++) {
+      const int d = 1 << s;
+      FpExt v = sh[cur][t];
+      if (t + d < 1024) v = ext_add(v, ext_mul(pw->Z[s], sh[cur][t + d]));
+      sh[cur ^ 1][t] = v;
+      cur ^= 1;
+      __syncthreads();
     }
+    // carry[b] = S_{t+1} + above * Z^(1023 - t); Z^(1023-t) from the binary expansion of the exponent
+    FpExt w = ext_one();
+    const int e = 1023 - t;
+    for (int s = 0; s < 10; s++)
+      if ((e >> s) & 1) w = ext_mul(w, pw->Z[s]);
+    FpExt cy = ext_mul(above, w);
+    if (t + 1 < 1024) cy = ext_add(cy, sh[cur][t + 1]);
+    if (b < nblocks) carry[b] = cy;
+    __syncthreads();
+    if (t == 0) above = ext_add(sh[cur][0], ext_mul(above, pw->Z[10]));
+    __syncthreads();
   }
 }
-__global__ void k_div_phase3(FpExt* p, size_t n, const FpExt* carry, FpExt z, FpExt* remainder) {
-  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t nchunks = (n + DIV_L - 1) / DIV_L;
-  if (c >= nchunks) return;
-  size_t lo = c * DIV_L, hi = lo + DIV_L < n ? lo + DIV_L : n;
-  FpExt cur = carry[c];
-  for (size_t j = hi; j-- > lo;) {
-    FpExt next = ext_add(ext_mul(z, cur), p[j]);
-    p[j] = cur;
-    cur = next;
+
+__global__ void __launch_bounds__(DIV_B) k_div_quotient(FpExt* p, size_t n, const FpExt* carry, const DivPowers* pw,
+                                                        FpExt* remainder) {
+  __shared__ FpExt sh[2][DIV_B];
+  const int t = threadIdx.x;
+  const size_t lo = ((size_t)blockIdx.x * DIV_B + t) * DIV_E;
+  const FpExt z = pw->z;
+  FpExt c[DIV_E];
+  int cur = 0;
+  sh[0][t] = div_local(p, n, lo, z, c);
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const int d = 1 << s;
+    FpExt v = sh[cur][t];
+    if (t + d < DIV_B) v = ext_add(v, ext_mul(pw->zs[s], sh[cur][t + d]));
+    sh[cur ^ 1][t] = v;
+    cur ^= 1;
+    __syncthreads();
   }
-  if (c == 0) *remainder = cur;
+  // value entering this thread's 8 coefficients from above
+  FpExt v = ext_mul(carry[blockIdx.x], pw->zt[t]);
+  if (t + 1 < DIV_B) v = ext_add(v, sh[cur][t + 1]);
+#pragma unroll
+  for (int j = DIV_E - 1; j >= 0; j--) {
+    const FpExt next = ext_add(ext_mul(z, v), c[j]);
+    if (lo + j < n) st_ext(p + lo + j, v);
+    v = next;
+  }
+  if (blockIdx.x == 0 && t == 0) *remainder = v;
 }
 
 __global__ void k_prefix_products(FpExt* io, size_t n) {  // test-only op in the reference; serial, exact
@@ -483,16 +541,35 @@ void r0_combos_prepare(Ctx* c, uint32_t* combos, const FpExt* coeff_u_host, size
 
 // poly: n FpExt coefficients, divided in place by (x - z); the remainder is written to *remainder_dev.
 void r0_poly_divide(Ctx* c, uint32_t* poly, size_t n, const FpExt& z, uint32_t* remainder_dev) {
-  PhaseScope ph(c, "combos_divide", 32.0 * (double)n);
   if (n == 0) return;
-  size_t nchunks = (n + DIV_L - 1) / DIV_L;
-  Scratch h(c, nchunks * sizeof(FpExt));
-  Scratch carry(c, nchunks * sizeof(FpExt));
-  FpExt zL = ext_pow(z, DIV_L);
-  unsigned blocks = (unsigned)((nchunks + 127) / 128);
-  k_div_phase1<<<blocks, 128, 0, c->stream>>>(h.as<FpExt>(), (const FpExt*)poly, n, z);
-  k_div_phase2<<<1, 256, 0, c->stream>>>(carry.as<FpExt>(), h.as<FpExt>(), nchunks, zL);
-  k_div_phase3<<<blocks, 128, 0, c->stream>>>((FpExt*)poly, n, carry.as<FpExt>(), z, (FpExt*)remainder_dev);
+  PhaseScope ph(c, "combos_divide", 32.0 * (double)n);
+  const size_t nblocks = (n + DIV_SEG - 1) / DIV_SEG;
+  R0_CHECK(nblocks <= (size_t(1) << DIV_MAXLG), "poly_divide: polynomial too long");
+  DivPowers pw;
+  pw.z = z;
+  FpExt z8 = ext_pow(z, DIV_E);
+  FpExt cur = z8;
+  for (int s = 0; s < 8; s++) {
+    pw.zs[s] = cur;
+    cur = ext_mul(cur, cur);
+  }
+  // cur = z^(8 * 256) = z^SEG
+  for (int s = 0; s <= DIV_MAXLG; s++) {
+    pw.Z[s] = cur;
+    cur = ext_mul(cur, cur);
+  }
+  FpExt acc = ext_one();
+  for (int t = DIV_B - 1; t >= 0; t--) {
+    pw.zt[t] = acc;
+    acc = ext_mul(acc, z8);
+  }
+  Scratch d_pw(c, &pw, sizeof(pw));
+  Scratch totals(c, nblocks * sizeof(FpExt));
+  Scratch carry(c, nblocks * sizeof(FpExt));
+  k_div_block_totals<<<(unsigned)nblocks, DIV_B, 0, c->stream>>>(totals.as<FpExt>(), (const FpExt*)poly, n, d_pw.as<DivPowers>());
+  k_div_block_carries<<<1, 1024, 0, c->stream>>>(carry.as<FpExt>(), totals.as<FpExt>(), nblocks, d_pw.as<DivPowers>());
+  k_div_quotient<<<(unsigned)nblocks, DIV_B, 0, c->stream>>>((FpExt*)poly, n, carry.as<FpExt>(), d_pw.as<DivPowers>(),
+                                                             (FpExt*)remainder_dev);
   count_launch(c, 3);
   R0_CUDA(cudaGetLastError());
 }

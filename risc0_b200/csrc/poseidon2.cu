@@ -214,6 +214,14 @@ void r0_p2_hash_fold(Ctx* c, uint32_t* io, size_t in_size, size_t out_size) {
 void r0_p2_merkle_fold_all(Ctx* c, uint32_t* nodes, size_t leaves) {
   PhaseScope ph(c, "hash_fold", 96.0 * (double)(leaves - 1));
   size_t in_size = leaves;
+  // wide levels: one full-width launch per level (every thread does exactly one permutation); the narrow top of the
+  // tree (<= 2^13 nodes per level, latency-bound) is folded several levels per launch
+  while (in_size > (size_t(1) << 14)) {
+    size_t out_size = in_size / 2;
+    p2_hash_fold_kernel<<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(nodes, in_size, out_size);
+    count_launch(c);
+    in_size = out_size;
+  }
   while (in_size > 1) {
     size_t out_size = in_size / 2;
     int B = out_size >= 256 ? 256 : (int)out_size;
