@@ -142,12 +142,10 @@ def main():
         torch.cuda.synchronize()
         hal.sync()
 
+    from risc0_b200 import shard
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(x, device="cuda")
 
     # ---- device-resident arm
     d_code, d_data, d_accum = hal.copy_from_elem("code", code), hal.copy_from_elem("data", data), hal.copy_from_elem("accum", accum)
@@ -190,8 +188,10 @@ def main():
     sampler.join(timeout=3)
 
     cycles = user_cycles(po2)
-    value = world * args.steps * cycles / (ms * 1e-3)
-    e2e_value = world * args.steps * cycles / (e2e_ms * 1e-3)
+    # every rank proved `steps` segments of `cycles` user cycles; whole-job value = all ranks' units / max time
+    units = shard.gather_counts(args.steps * cycles, device="cuda")
+    value = shard.whole_job_throughput(units, ms * 1e-3)
+    e2e_value = shard.whole_job_throughput(units, e2e_ms * 1e-3)
 
     # ---- roofline of the dominant kernel family (device time from the events recorded around each launch)
     peaks = {}
