@@ -398,8 +398,10 @@ def flatten_sums(S, outs):
             sg, x, is_root = st.pop()
             k = S.nodes[x]
             if (is_root or uses[x] == 1) and k[0] in "+-":
-                st.append((sg, k[1], False))
+                # push right first so that the left operand (the earlier part of the chain) is visited first:
+                # the leaves come out in the generator's original constraint order, which has good operand locality
                 st.append((sg if k[0] == "+" else -sg, k[2], False))
+                st.append((sg, k[1], False))
             elif (is_root or uses[x] == 1) and k[0] == "n":
                 st.append((-sg, k[1], False))
             else:
@@ -517,7 +519,7 @@ class Ptx:
         self.pos = 0
         self.remat = int(os.environ.get("EVAL_REMAT_DIST", "400"))   # re-load / recompute instead of keeping alive
         self.remat_cost = int(os.environ.get("EVAL_REMAT_COST", "8"))
-        self.split = int(os.environ.get("EVAL_SPLIT", "0"))
+        self.split = int(os.environ.get("EVAL_SPLIT", "400"))
         self.last_fence = 0
         self.use_bar = os.environ.get("EVAL_BAR", "0") == "1"
         self.bases = {}
@@ -730,7 +732,10 @@ class Ptx:
                 keyed.setdefault(key, []).append((d, a, b))
         acc = {d: None for d in dots}
         bound = {d: 0 for d in dots}
-        order = sorted(keyed, key=lambda key: -max([self.weight[x] for x in key] or [0]))
+        if os.environ.get("EVAL_ORDER", "program") == "weight":
+            order = sorted(keyed, key=lambda key: -max([self.weight[x] for x in key] or [0]))
+        else:
+            order = list(keyed)    # first-appearance order = the constraint system's own order
         for key in order:
             for x in sorted(key, key=lambda x: -self.weight[x]):
                 self.ensure(x)
