@@ -79,6 +79,9 @@ def run_reference(args, rank, world):
     """CPU prover on the host cores (rank 0 only). Each step proves one bounded-size segment."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU prover is meant to use every host core (the reference uses rayon
+    # over all cores), so override it before libgomp is loaded
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     po2 = args.cpu_po2
@@ -217,6 +220,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O
         cp = args.cpu_po2
