@@ -19,6 +19,14 @@ namespace r0 {
 __constant__ uint32_t c_rc_full[8 * 24];
 __constant__ uint32_t c_rc_partial[21];
 __constant__ uint32_t c_diag[24];
+__constant__ uint32_t c_one;  // = 1, opaque to the compiler: a * c_one + b is an IMAD, i.e. an add on the fma pipe
+
+// The permutation is bound by the alu pipe (every modular add / product ends in a VIADDMNMX there), while the fma pipe
+// is half idle; adds in the linear layer are therefore issued as IMAD (x * 1 + y) to balance the two pipes.
+__device__ __forceinline__ uint32_t fp_add_fma(uint32_t a, uint32_t b) {
+  uint32_t r = a * c_one + b;
+  return umin32(r, r - P);
+}
 
 __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
   uint32_t x2 = fp_mul(x, x);
@@ -27,6 +35,7 @@ __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
   return fp_mul(x6, x);
 }
 __device__ __forceinline__ uint32_t dbl(uint32_t x) { return fp_add(x, x); }
+__device__ __forceinline__ uint32_t dbl_fma(uint32_t x) { return fp_add_fma(x, x); }
 
 // M_ext = circ(2*M4, M4, ..., M4) with M4 the 4x4 matrix of poseidon2/mod.rs:139-151
 __device__ __forceinline__ void m_ext(uint32_t (&c)[24]) {
@@ -34,29 +43,29 @@ __device__ __forceinline__ void m_ext(uint32_t (&c)[24]) {
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     uint32_t x0 = c[4 * i], x1 = c[4 * i + 1], x2 = c[4 * i + 2], x3 = c[4 * i + 3];
-    uint32_t t0 = fp_add(x0, x1);
-    uint32_t t1 = fp_add(x2, x3);
-    uint32_t t2 = fp_add(dbl(x1), t1);
-    uint32_t t3 = fp_add(dbl(x3), t0);
-    uint32_t t4 = fp_add(dbl(dbl(t1)), t3);
-    uint32_t t5 = fp_add(dbl(dbl(t0)), t2);
-    uint32_t t6 = fp_add(t3, t5);
-    uint32_t t7 = fp_add(t2, t4);
+    uint32_t t0 = fp_add_fma(x0, x1);
+    uint32_t t1 = fp_add_fma(x2, x3);
+    uint32_t t2 = fp_add_fma(dbl_fma(x1), t1);
+    uint32_t t3 = fp_add_fma(dbl_fma(x3), t0);
+    uint32_t t4 = fp_add_fma(dbl_fma(dbl_fma(t1)), t3);
+    uint32_t t5 = fp_add_fma(dbl_fma(dbl_fma(t0)), t2);
+    uint32_t t6 = fp_add_fma(t3, t5);
+    uint32_t t7 = fp_add_fma(t2, t4);
     c[4 * i] = t6;
     c[4 * i + 1] = t5;
     c[4 * i + 2] = t7;
     c[4 * i + 3] = t4;
-    s0 = fp_add(s0, t6);
-    s1 = fp_add(s1, t5);
-    s2 = fp_add(s2, t7);
-    s3 = fp_add(s3, t4);
+    s0 = fp_add_fma(s0, t6);
+    s1 = fp_add_fma(s1, t5);
+    s2 = fp_add_fma(s2, t7);
+    s3 = fp_add_fma(s3, t4);
   }
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    c[4 * i] = fp_add(c[4 * i], s0);
-    c[4 * i + 1] = fp_add(c[4 * i + 1], s1);
-    c[4 * i + 2] = fp_add(c[4 * i + 2], s2);
-    c[4 * i + 3] = fp_add(c[4 * i + 3], s3);
+    c[4 * i] = fp_add_fma(c[4 * i], s0);
+    c[4 * i + 1] = fp_add_fma(c[4 * i + 1], s1);
+    c[4 * i + 2] = fp_add_fma(c[4 * i + 2], s2);
+    c[4 * i + 3] = fp_add_fma(c[4 * i + 3], s3);
   }
 }
 
@@ -71,12 +80,15 @@ __device__ __forceinline__ void partial_round(uint32_t (&c)[24], int r) {
   // sum of 24 canonical values: pairwise tree keeps the dependency chain short
   uint32_t p[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) p[i] = fp_add(c[2 * i], c[2 * i + 1]);
+  for (int i = 0; i < 12; i++) p[i] = fp_add_fma(c[2 * i], c[2 * i + 1]);
 #pragma unroll
-  for (int i = 0; i < 6; i++) p[i] = fp_add(p[2 * i], p[2 * i + 1]);
-  uint32_t sum = fp_add(fp_add(fp_add(p[0], p[1]), fp_add(p[2], p[3])), fp_add(p[4], p[5]));
+  for (int i = 0; i < 6; i++) p[i] = fp_add_fma(p[2 * i], p[2 * i + 1]);
+  uint32_t sum = fp_add_fma(fp_add_fma(fp_add_fma(p[0], p[1]), fp_add_fma(p[2], p[3])), fp_add_fma(p[4], p[5]));
+  // sum + diag_i * c_i as one Montgomery reduction: sum enters the 64-bit product as sum * 2^32 mod P (MONT_ONE), so the
+  // total stays below P * 2^32 and the separate modular add disappears
+  const uint64_t s64 = (uint64_t)sum * MONT_ONE;
 #pragma unroll
-  for (int i = 0; i < 24; i++) c[i] = fp_add(sum, fp_mul(c_diag[i], c[i]));
+  for (int i = 0; i < 24; i++) c[i] = mont_reduce((uint64_t)c_diag[i] * c[i] + s64);
 }
 
 __device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) {
@@ -189,6 +201,8 @@ void r0_poseidon2_init(Ctx* c) {
                                   cudaMemcpyHostToDevice, c->stream));
   R0_CUDA(cudaMemcpyToSymbolAsync(c_diag, R0_P2_DIAG_MONT, sizeof(R0_P2_DIAG_MONT), 0, cudaMemcpyHostToDevice,
                                   c->stream));
+  const uint32_t one = 1;
+  R0_CUDA(cudaMemcpyToSymbolAsync(c_one, &one, sizeof(one), 0, cudaMemcpyHostToDevice, c->stream));
   R0_CUDA(cudaStreamSynchronize(c->stream));
 }
 
