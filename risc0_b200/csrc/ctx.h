@@ -48,6 +48,7 @@ struct Tables {
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host->device witness uploads, overlapped with compute on `stream`
   int sm_count = 148;
   Tables tab{};
   uint64_t launches = 0;       // kernels launched through this context (bench.py's gpu_launches)

@@ -26,6 +26,7 @@ r0b200_err r0b200_create(int device, r0b200_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   R0_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  R0_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   // keep freed blocks in the stream-ordered pool instead of returning them to the OS between proofs
   cudaMemPool_t pool;
   R0_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -49,6 +50,7 @@ void r0b200_destroy(r0b200_ctx* c) {
   for (auto& e : c->event_pool) cudaEventDestroy(e);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -204,18 +204,55 @@ class SegmentProver {
   std::vector<Digest> roots;
   std::vector<uint32_t> query_pos;
 
-  // Prover::commit_group (prover.rs:81-108). `witness` may be a host or a device pointer.
-  void commit_group(size_t g, const uint32_t* witness, bool on_host) {
+  // Host-resident witness: allocate the group's coefficient buffer now and enqueue its upload on the copy stream in
+  // chunks of columns, one event per chunk. commit_group() later makes the compute stream wait chunk by chunk, so the
+  // PCIe transfer of chunk j+1 (and of the next group) overlaps the NTTs / hashing of what is already on the device.
+  void prefetch_group(size_t g, const uint32_t* witness_host) {
     const size_t count = taps_.group_sizes[g];
     PolyGroup& pg = groups_[g];
     pg.count = count;
     pg.coeffs = DevBuf(c_, count * cycles_);
-    if (on_host) {
-      R0_CUDA(cudaMemcpyAsync(pg.coeffs.p, witness, count * cycles_ * 4, cudaMemcpyHostToDevice, c_->stream));
-    } else {
-      r0_eltwise_copy(c_, pg.coeffs.p, witness, count * cycles_);
+    cudaEvent_t ready;
+    R0_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    R0_CUDA(cudaEventRecord(ready, c_->stream));            // the allocation is ordered on the compute stream
+    R0_CUDA(cudaStreamWaitEvent(c_->copy_stream, ready, 0));
+    R0_CUDA(cudaEventDestroy(ready));
+    const size_t chunk = upload_chunk_cols();
+    for (size_t c0 = 0; c0 < count; c0 += chunk) {
+      const size_t nc = std::min(chunk, count - c0);
+      R0_CUDA(cudaMemcpyAsync(pg.coeffs.p + c0 * cycles_, witness_host + c0 * cycles_, nc * cycles_ * 4,
+                              cudaMemcpyHostToDevice, c_->copy_stream));
+      cudaEvent_t ev;
+      R0_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      R0_CUDA(cudaEventRecord(ev, c_->copy_stream));
+      uploads_[g].push_back(ev);
     }
-    r0_ntt_interpolate(c_, pg.coeffs.p, count, (int)po2_, /*zk=*/true, 0);
+  }
+  size_t upload_chunk_cols() const {
+    size_t cols = (size_t(64) << 20) / (cycles_ * 4);   // about 64 MB per chunk
+    return cols ? cols : 1;
+  }
+
+  // Prover::commit_group (prover.rs:81-108). `witness` is a device pointer, or NULL when prefetch_group() was used.
+  void commit_group(size_t g, const uint32_t* witness_dev) {
+    const size_t count = taps_.group_sizes[g];
+    PolyGroup& pg = groups_[g];
+    if (witness_dev) {
+      pg.count = count;
+      pg.coeffs = DevBuf(c_, count * cycles_);
+      r0_eltwise_copy(c_, pg.coeffs.p, witness_dev, count * cycles_);
+      r0_ntt_interpolate(c_, pg.coeffs.p, count, (int)po2_, /*zk=*/true, 0);
+    } else {
+      const size_t chunk = upload_chunk_cols();
+      size_t j = 0;
+      for (size_t c0 = 0; c0 < count; c0 += chunk, j++) {
+        const size_t nc = std::min(chunk, count - c0);
+        R0_CUDA(cudaStreamWaitEvent(c_->stream, uploads_[g][j], 0));
+        R0_CUDA(cudaEventDestroy(uploads_[g][j]));
+        r0_ntt_interpolate(c_, pg.coeffs.p + c0 * cycles_, nc, (int)po2_, /*zk=*/true, 0);
+      }
+      uploads_[g].clear();
+    }
     finish_group(pg);
     pg.merkle.commit(c_, iop_, &roots);
   }
@@ -397,6 +434,7 @@ class SegmentProver {
   HostSuite suite_;
   TapSet taps_;
   std::vector<PolyGroup> groups_;
+  std::vector<cudaEvent_t> uploads_[3];
 };
 
 }  // namespace
@@ -432,11 +470,18 @@ extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po
   header[RV32IM_OUTPUT_SIZE] = po2;
   iop.commit(suite.hash_words(header, RV32IM_OUTPUT_SIZE + 1));
   iop.write(header, RV32IM_OUTPUT_SIZE + 1);
-  prover.commit_group(1, code, witness_on_host != 0);
-  prover.commit_group(2, data, witness_on_host != 0);
+  const bool on_host = witness_on_host != 0;
+  if (on_host) {
+    // uploads are enqueued up front in consumption order; each group's compute waits only for its own chunks
+    prover.prefetch_group(1, code);
+    prover.prefetch_group(2, data);
+    prover.prefetch_group(0, accum);
+  }
+  prover.commit_group(1, on_host ? nullptr : code);
+  prover.commit_group(2, on_host ? nullptr : data);
   uint32_t mix[RV32IM_MIX_SIZE];
   for (size_t i = 0; i < RV32IM_MIX_SIZE; i++) mix[i] = iop.random_elem();
-  prover.commit_group(0, accum, witness_on_host != 0);
+  prover.commit_group(0, on_host ? nullptr : accum);
   prover.finalize(mix, header);
   R0_CUDA(cudaStreamSynchronize(ctx->stream));
   if (seal_len) *seal_len = iop.proof.size();

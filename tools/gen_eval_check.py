@@ -1023,3 +1023,35 @@ if __name__ == "__main__":
     t = threading.Thread(target=main)
     t.start()
     t.join()
+
+
+# ------------------------------------------------------------------------------------------------ reference evaluator
+def evaluate_scalars(S, outs, tap, cst):
+    """Pure-python evaluation of a lowered scalar DAG (Montgomery words, exact integer arithmetic) - used by the CPU
+    test-suite to check the generator's lowering / flattening against the reference poly_fp without a GPU.
+    tap(buf, col, back) -> Montgomery word of that tap at the point under evaluation; cst(offset) -> constant word."""
+    val = [None] * len(S.nodes)
+    for i, k in enumerate(S.nodes):
+        o = k[0]
+        if o == "i":
+            v = k[1]
+        elif o == "k":
+            v = cst(k[1])
+        elif o == "t":
+            v = tap(k[1], k[2], k[3])
+        elif o == "+":
+            v = (val[k[1]] + val[k[2]]) % P
+        elif o == "-":
+            v = (val[k[1]] - val[k[2]]) % P
+        elif o == "n":
+            v = (-val[k[1]]) % P
+        elif o == "N":
+            v = P - val[k[1]]          # lazy negation: may equal P, only ever used inside a product
+        elif o == "*":
+            v = val[k[1]] * val[k[2]] * RINV % P
+        elif o == "d":
+            v = sum(val[a] * val[b] for a, b in k[1]) * RINV % P
+        else:
+            raise ValueError(k)
+        val[i] = v
+    return [val[o] for o in outs]
