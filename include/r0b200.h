@@ -132,6 +132,12 @@ r0b200_err r0b200_eval_check_rv32im(r0b200_ctx* ctx, uint32_t* check, const uint
                                     const uint32_t* accum, const uint32_t* mix, const uint32_t* out,
                                     const uint32_t* poly_mix_host, uint32_t po2);
 
+/* Same for the recursion circuit (risc0_circuit_recursion_cpu_eval_check, recursion-sys/kernels/cxx/ffi.cpp:219-246;
+ * recursion/src/prove/hal/cpu.rs:106-150): ctrl 23, data 128, accum 12 columns; mix 20 words, out 32 words. */
+r0b200_err r0b200_eval_check_recursion(r0b200_ctx* ctx, uint32_t* check, const uint32_t* ctrl, const uint32_t* data,
+                                       const uint32_t* accum, const uint32_t* mix, const uint32_t* out,
+                                       const uint32_t* poly_mix_host, uint32_t po2);
+
 /* ---- whole segment (the Hal's caller on the hot path) ---- */
 /* prove_core's prove_inner block for a committed rv32im witness (rv32im/src/prove/hal/mod.rs:171-222 ->
  * zkp/src/prove/prover.rs:81-393 -> prove/fri.rs:77-126): commits code (1 x N), data (211 x N), accum (103 x N),
@@ -143,6 +149,14 @@ r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const ui
                                const uint32_t* accum, int witness_on_host, const uint32_t* global_host,
                                uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
                                size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host);
+
+/* RecursionProverImpl::prove's prove block (recursion/src/prove/mod.rs:179-224) for a committed witness: ctrl
+ * (23 x N), data (128 x N), accum (12 x N), global_host 32 words; lift / join / resolve programs all have this shape
+ * (po2 = 18 by default). No seal version word. */
+r0b200_err r0b200_prove_recursion(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* ctrl, const uint32_t* data,
+                                  const uint32_t* accum, int witness_on_host, const uint32_t* global_host,
+                                  uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
+                                  size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host);
 
 #ifdef __cplusplus
 }

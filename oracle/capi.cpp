@@ -13,6 +13,7 @@
 
 #include "hal_cpu.h"
 #include "prover.h"
+#include "tables/circuit_recursion.h"
 #include "tables/circuit_rv32im.h"
 #include "verifier.h"
 
@@ -362,6 +363,117 @@ extern "C" const char* orc_verify_rv32im(int hash_kind, const uint32_t* seal, ui
   if (n == 0 || seal[0] != RV32IM_SEAL_VERSION) throw VerifyError("bad seal version word");
   Verifier* v = nullptr;
   verify_standard(taps, suite, seal, n, RV32IM_CIRCUIT_INFO, RV32IM_OUTPUT_SIZE, RV32IM_MIX_SIZE, 1, PolyExtFn(), &v);
+  if (nroots) *nroots = v->roots.size();
+  if (roots_out) memcpy(roots_out, v->roots.data(), v->roots.size() * 32);
+  ORC_CATCH
+}
+
+// ------------------------------------------------------------------ recursion circuit
+// reference-compiled poly_fp through oracle/ref_shim_recursion.cpp
+static rv32im_poly_fp_t g_recursion_poly_fp = nullptr;
+extern "C" const char* orc_load_ref_recursion(const char* path) {
+  ORC_TRY
+  void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) throw std::runtime_error(std::string("dlopen failed: ") + dlerror());
+  g_recursion_poly_fp = (rv32im_poly_fp_t)dlsym(h, "r0ref_recursion_poly_fp");
+  if (!g_recursion_poly_fp) throw std::runtime_error("symbol r0ref_recursion_poly_fp not found");
+  ORC_CATCH
+}
+extern "C" int orc_ref_recursion_loaded() { return g_recursion_poly_fp != nullptr; }
+
+static TapSet recursion_taps() {
+  return TapSet::from_tables(RECURSION_TAPS, RECURSION_NUM_TAPS, RECURSION_COMBO_TAPS, RECURSION_TOT_COMBO_BACKS,
+                             RECURSION_COMBO_BEGIN, RECURSION_NUM_COMBOS, RECURSION_GROUP_BEGIN, 3, RECURSION_NUM_REGS);
+}
+
+// recursion CpuCircuitHal::eval_check (recursion/src/prove/hal/cpu.rs:106-150 ->
+// risc0_circuit_recursion_cpu_eval_check, recursion-sys/kernels/cxx/ffi.cpp:219-246): args = ctrl, global, data, mix, accum
+static void recursion_eval_check(Fp* check, const Fp* ctrl, const Fp* data, const Fp* accum, const Fp* mix,
+                                 const Fp* global, FpExt poly_mix, size_t po2, size_t steps, size_t begin, size_t end) {
+  if (!g_recursion_poly_fp) throw std::runtime_error("oracle/_ref recursion poly_fp not loaded");
+  size_t domain = steps * INV_RATE;
+  std::vector<FpExt> pows(RECURSION_NUM_POLY_MIX_POWERS);
+  for (size_t i = 0; i < pows.size(); i++) pows[i] = poly_mix.pow(RECURSION_POLY_MIX_POWERS[i]);
+  Fp rou = rou_fwd(unsigned(po2 + 2));
+  std::string err;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (size_t cycle = begin; cycle < end; cycle++) {
+    Fp* args[5] = {const_cast<Fp*>(ctrl), const_cast<Fp*>(global), const_cast<Fp*>(data), const_cast<Fp*>(mix),
+                   const_cast<Fp*>(accum)};
+    FpExt tot;
+    const char* e = g_recursion_poly_fp(cycle, domain, pows.data(), args, &tot);
+    if (e) {
+#pragma omp critical
+      err = e;
+      continue;
+    }
+    Fp x = rou.pow(cycle);
+    Fp y = (Fp(3) * x).pow(size_t(1) << po2);
+    FpExt ret = tot * (y - Fp(1)).inv();
+    for (size_t k = 0; k < EXT_SIZE; k++) check[k * domain + cycle] = ret.e[k];
+  }
+  if (!err.empty()) throw std::runtime_error(err);
+}
+extern "C" const char* orc_recursion_eval_check(uint32_t* check, const uint32_t* ctrl, const uint32_t* data,
+                                                const uint32_t* accum, const uint32_t* mix, const uint32_t* global,
+                                                const uint32_t* poly_mix, uint32_t po2, uint64_t begin, uint64_t end) {
+  ORC_TRY
+  FpExt pm(Fp::raw(poly_mix[0]), Fp::raw(poly_mix[1]), Fp::raw(poly_mix[2]), Fp::raw(poly_mix[3]));
+  recursion_eval_check((Fp*)check, (const Fp*)ctrl, (const Fp*)data, (const Fp*)accum, (const Fp*)mix, (const Fp*)global,
+                       pm, po2, size_t(1) << po2, begin, end);
+  ORC_CATCH
+}
+
+// RecursionProverImpl::prove's prove block (recursion/src/prove/mod.rs:179-224) for a GIVEN witness: ctrl (23 x N),
+// data (128 x N), accum (12 x N), global (32). No version word (the rv32im crate adds one, recursion does not).
+extern "C" const char* orc_prove_recursion(int hash_kind, uint32_t po2, const uint32_t* ctrl, const uint32_t* data,
+                                           const uint32_t* accum, const uint32_t* global, uint32_t* seal_out,
+                                           uint64_t seal_cap, uint64_t* seal_len, uint32_t* roots_out, uint64_t roots_cap,
+                                           uint64_t* nroots, uint32_t* qpos_out) {
+  ORC_TRY
+  HashSuite suite = suite_of(hash_kind);
+  TapSet taps = recursion_taps();
+  size_t N = size_t(1) << po2;
+  SealOut so;
+  Prover prover(suite, taps);
+  prover.trace = &so.trace;
+  auto info16 = [&](const char* s) {
+    Fp e[16];
+    for (int i = 0; i < 16; i++) e[i] = Fp(uint32_t(uint8_t(s[i])));
+    prover.iop.commit(suite.hash_elem_slice(e, 16));
+  };
+  info16("RISC0_STARK:v1__");
+  info16(RECURSION_CIRCUIT_INFO);
+  std::vector<Fp> header(RECURSION_OUTPUT_SIZE + 1);
+  std::vector<Fp> glob(RECURSION_OUTPUT_SIZE);
+  for (size_t i = 0; i < RECURSION_OUTPUT_SIZE; i++) header[i] = glob[i] = Fp::raw(global[i]).valid_or_zero();
+  header[RECURSION_OUTPUT_SIZE] = Fp::raw(po2);
+  prover.iop.commit(suite.hash_elem_slice(header.data(), header.size()));
+  prover.iop.write_elems(header.data(), header.size());
+  prover.set_po2(po2);
+  prover.commit_group(1, (const Fp*)ctrl, N * RECURSION_GROUP_SIZES[1]);
+  prover.commit_group(2, (const Fp*)data, N * RECURSION_GROUP_SIZES[2]);
+  std::vector<Fp> mix(RECURSION_MIX_SIZE);
+  for (auto& m : mix) m = prover.iop.random_elem();
+  prover.commit_group(0, (const Fp*)accum, N * RECURSION_GROUP_SIZES[0]);
+  EvalCheckFn ec = [&](Fp* check, const std::vector<const Fp*>& g, const std::vector<const Fp*>& globals, FpExt pm,
+                       size_t p2, size_t steps) {
+    recursion_eval_check(check, g[1], g[2], g[0], globals[0], globals[1], pm, p2, steps, 0, steps * INV_RATE);
+  };
+  so.seal = prover.finalize({mix.data(), glob.data()}, ec);
+  const char* e = finish(&so, seal_out, seal_cap, seal_len, roots_out, roots_cap, nroots, qpos_out);
+  if (e) return e;
+  ORC_CATCH
+}
+
+// recursion seal: Merkle / FRI / DEEP consistency (poly_ext.rs is present in the reference but not restated here)
+extern "C" const char* orc_verify_recursion(int hash_kind, const uint32_t* seal, uint64_t n, uint32_t* roots_out,
+                                            uint64_t* nroots) {
+  ORC_TRY
+  HashSuite suite = suite_of(hash_kind);
+  TapSet taps = recursion_taps();
+  Verifier* v = nullptr;
+  verify_standard(taps, suite, seal, n, RECURSION_CIRCUIT_INFO, RECURSION_OUTPUT_SIZE, RECURSION_MIX_SIZE, 0, PolyExtFn(), &v);
   if (nroots) *nroots = v->roots.size();
   if (roots_out) memcpy(roots_out, v->roots.data(), v->roots.size() * 32);
   ORC_CATCH

@@ -45,7 +45,7 @@ def generate(force=False):
     """(re)create csrc/gen/* from the committed circuit IR when missing or stale (tools/gen_eval_check.py)"""
     root = os.path.join(HERE, "..")
     gen = os.path.join(root, "tools", "gen_eval_check.py")
-    for name in ("rv32im",):
+    for name in ("rv32im", "recursion"):
         irf = os.path.join(HERE, "circuits", name + ".ir.json.gz")
         launcher = os.path.join(CSRC, "gen", "eval_check_%s.cu" % name)
         ptx = glob.glob(os.path.join(CSRC, "gen", "eval_check_%s_p*.ptx" % name))

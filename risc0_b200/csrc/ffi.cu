@@ -8,6 +8,16 @@
 
 using namespace r0;
 
+// the Hal passes mix / out as device buffers; the kernels take them in the parameter block (constant bank)
+template <size_t MIX, size_t OUT, typename F>
+static void eval_check_with_device_globals(r0b200_ctx* ctx, const uint32_t* mix, const uint32_t* out, F launch) {
+  uint32_t host[MIX + OUT];
+  R0_CUDA(cudaMemcpyAsync(host, mix, MIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  R0_CUDA(cudaMemcpyAsync(host + MIX, out, OUT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  R0_CUDA(cudaStreamSynchronize(ctx->stream));
+  launch(host + MIX, host);
+}
+
 extern "C" {
 
 r0b200_err r0b200_create(int device, r0b200_ctx** out) {
@@ -325,13 +335,19 @@ r0b200_err r0b200_eval_check_rv32im(r0b200_ctx* ctx, uint32_t* check, const uint
                                     const uint32_t* accum, const uint32_t* mix, const uint32_t* out,
                                     const uint32_t* poly_mix_host, uint32_t po2) {
   CTX_BEGIN
-  (void)ctrl;
-  // the Hal passes mix / out as device buffers; the kernels take them in the parameter block (constant bank)
-  uint32_t host[36 + 90];
-  R0_CUDA(cudaMemcpyAsync(host, mix, 36 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  R0_CUDA(cudaMemcpyAsync(host + 36, out, 90 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  R0_CUDA(cudaStreamSynchronize(ctx->stream));
-  r0_eval_check_rv32im(ctx, check, accum, data, host + 36, host, ext_from_host(poly_mix_host), po2);
+  eval_check_with_device_globals<36, 90>(ctx, mix, out, [&](const uint32_t* out_host, const uint32_t* mix_host) {
+    r0_eval_check_rv32im(ctx, check, accum, ctrl, data, out_host, mix_host, ext_from_host(poly_mix_host), po2);
+  });
+  R0_API_END
+}
+
+r0b200_err r0b200_eval_check_recursion(r0b200_ctx* ctx, uint32_t* check, const uint32_t* ctrl, const uint32_t* data,
+                                       const uint32_t* accum, const uint32_t* mix, const uint32_t* out,
+                                       const uint32_t* poly_mix_host, uint32_t po2) {
+  CTX_BEGIN
+  eval_check_with_device_globals<20, 32>(ctx, mix, out, [&](const uint32_t* out_host, const uint32_t* mix_host) {
+    r0_eval_check_recursion(ctx, check, accum, ctrl, data, out_host, mix_host, ext_from_host(poly_mix_host), po2);
+  });
   R0_API_END
 }
 

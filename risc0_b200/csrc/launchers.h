@@ -52,5 +52,8 @@ void r0_gather_batched(r0::Ctx* c, uint32_t* dst, const GatherJob* jobs_host, si
 void r0_gather_digests(r0::Ctx* c, uint32_t* dst, const DigestJob* jobs_host, size_t njobs);
 
 // generated circuit kernels (csrc/gen/, tools/gen_eval_check.py)
-void r0_eval_check_rv32im(r0::Ctx* c, uint32_t* check, const uint32_t* accum, const uint32_t* data,
+void r0_eval_check_rv32im(r0::Ctx* c, uint32_t* check, const uint32_t* accum, const uint32_t* code, const uint32_t* data,
                           const uint32_t* global_host, const uint32_t* mix_host, const r0::FpExt& poly_mix, uint32_t po2);
+void r0_eval_check_recursion(r0::Ctx* c, uint32_t* check, const uint32_t* accum, const uint32_t* code,
+                             const uint32_t* data, const uint32_t* global_host, const uint32_t* mix_host,
+                             const r0::FpExt& poly_mix, uint32_t po2);

@@ -20,6 +20,7 @@
 #include "../../include/r0b200.h"
 #include "ctx.h"
 #include "launchers.h"
+#include "tables/circuit_recursion.h"
 #include "tables/circuit_rv32im.h"
 #include "tables/field_tables.h"
 #include "transcript.h"
@@ -79,17 +80,45 @@ struct TapSet {
   }
 };
 
-TapSet rv32im_taps() {
+// Everything circuit-specific the driver needs: tap set, sizes, the info string hashed into the transcript, whether
+// a seal version word is written first (rv32im/src/prove/hal/mod.rs:181-183 does, the recursion prover does not,
+// recursion/src/prove/mod.rs:179-224), and the circuit's eval_check launcher.
+struct CircuitDesc {
+  const char* info;
+  const uint16_t* taps;
+  size_t ntaps;
+  const uint16_t* combo_taps;
+  size_t ncombo_taps;
+  const uint16_t* combo_begin;
+  size_t ncombos;
+  const uint32_t* group_begin;
+  const uint32_t* group_sizes;
+  size_t output_size, mix_size;
+  bool has_version;
+  uint32_t version;
+  void (*eval_check)(Ctx*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*,
+                     const FpExt&, uint32_t);
+};
+
+const CircuitDesc kRv32im = {RV32IM_CIRCUIT_INFO, RV32IM_TAPS, RV32IM_NUM_TAPS, RV32IM_COMBO_TAPS, RV32IM_TOT_COMBO_BACKS,
+                             RV32IM_COMBO_BEGIN, RV32IM_NUM_COMBOS, RV32IM_GROUP_BEGIN, RV32IM_GROUP_SIZES,
+                             RV32IM_OUTPUT_SIZE, RV32IM_MIX_SIZE, true, RV32IM_SEAL_VERSION, r0_eval_check_rv32im};
+const CircuitDesc kRecursion = {RECURSION_CIRCUIT_INFO, RECURSION_TAPS, RECURSION_NUM_TAPS, RECURSION_COMBO_TAPS,
+                                RECURSION_TOT_COMBO_BACKS, RECURSION_COMBO_BEGIN, RECURSION_NUM_COMBOS,
+                                RECURSION_GROUP_BEGIN, RECURSION_GROUP_SIZES, RECURSION_OUTPUT_SIZE, RECURSION_MIX_SIZE,
+                                false, 0, r0_eval_check_recursion};
+
+TapSet make_taps(const CircuitDesc& d) {
   TapSet t;
-  for (size_t i = 0; i < RV32IM_NUM_TAPS; i++) {
-    const uint16_t* f = RV32IM_TAPS + 5 * i;
+  for (size_t i = 0; i < d.ntaps; i++) {
+    const uint16_t* f = d.taps + 5 * i;
     t.taps.push_back({f[0], f[1], f[2], f[3], f[4]});
   }
-  t.combo_taps.assign(RV32IM_COMBO_TAPS, RV32IM_COMBO_TAPS + RV32IM_TOT_COMBO_BACKS);
-  t.combo_begin.assign(RV32IM_COMBO_BEGIN, RV32IM_COMBO_BEGIN + RV32IM_NUM_COMBOS + 1);
-  t.group_begin.assign(RV32IM_GROUP_BEGIN, RV32IM_GROUP_BEGIN + 4);
-  t.group_sizes.assign(RV32IM_GROUP_SIZES, RV32IM_GROUP_SIZES + 3);
-  t.combos_count = RV32IM_NUM_COMBOS;
+  t.combo_taps.assign(d.combo_taps, d.combo_taps + d.ncombo_taps);
+  t.combo_begin.assign(d.combo_begin, d.combo_begin + d.ncombos + 1);
+  t.group_begin.assign(d.group_begin, d.group_begin + 4);
+  t.group_sizes.assign(d.group_sizes, d.group_sizes + 3);
+  t.combos_count = d.ncombos;
   return t;
 }
 
@@ -197,7 +226,8 @@ struct PolyGroup {
 
 class SegmentProver {
  public:
-  SegmentProver(Ctx* c, int hash, size_t po2) : c_(c), hash_(hash), po2_(po2), cycles_(size_t(1) << po2), iop_(hash), suite_{hash}, taps_(rv32im_taps()) {
+  SegmentProver(Ctx* c, const CircuitDesc& desc, int hash, size_t po2)
+      : c_(c), desc_(desc), hash_(hash), po2_(po2), cycles_(size_t(1) << po2), iop_(hash), suite_{hash}, taps_(make_taps(desc)) {
     groups_.resize(taps_.num_groups());
   }
   Transcript& iop() { return iop_; }
@@ -264,8 +294,8 @@ class SegmentProver {
     PolyGroup check;
     check.count = CHECK_SIZE;
     check.coeffs = DevBuf(c_, EXT * domain);
-    r0_eval_check_rv32im(c_, check.coeffs.p, groups_[0].evaluated.p, groups_[2].evaluated.p, out_host, mix_host, poly_mix,
-                         (uint32_t)po2_);
+    desc_.eval_check(c_, check.coeffs.p, groups_[0].evaluated.p, groups_[1].evaluated.p, groups_[2].evaluated.p, out_host,
+                     mix_host, poly_mix, (uint32_t)po2_);
     r0_ntt_interpolate(c_, check.coeffs.p, EXT, (int)(po2_ + 2), /*zk=*/false, 0);
     finish_group(check);
     check.merkle.commit(c_, iop_, &roots);
@@ -428,6 +458,7 @@ class SegmentProver {
   }
 
   Ctx* c_;
+  const CircuitDesc& desc_;
   int hash_;
   size_t po2_, cycles_;
   Transcript iop_;
@@ -442,34 +473,32 @@ class SegmentProver {
 
 using namespace r0;
 
-extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* code,
-                                          const uint32_t* data, const uint32_t* accum, int witness_on_host,
-                                          const uint32_t* global_host, uint32_t* seal_out_host, size_t seal_cap,
-                                          size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
-                                          uint32_t* query_pos_out_host) {
-  R0_API_BEGIN
+static void prove_segment(r0b200_ctx* ctx, const CircuitDesc& desc, int hash, uint32_t po2, const uint32_t* code,
+                          const uint32_t* data, const uint32_t* accum, int witness_on_host, const uint32_t* global_host,
+                          uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
+                          size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host) {
   R0_CHECK(ctx != nullptr, "null r0b200 context");
   R0_CUDA(cudaSetDevice(ctx->device));
   R0_CHECK(hash == R0B200_HASH_POSEIDON2 || hash == R0B200_HASH_SHA256, "prove: unknown hash suite");
-  R0_CHECK(po2 >= 9 && po2 + 2 <= (uint32_t)MAX_LG, "prove: po2 out of range (ZK_CYCLES = 1024 needs po2 >= 9... <= 22)");
-  SegmentProver prover(ctx, hash, po2);
+  R0_CHECK(po2 >= 9 && po2 + 2 <= (uint32_t)MAX_LG, "prove: po2 out of range (9..22)");
+  SegmentProver prover(ctx, desc, hash, po2);
   Transcript& iop = prover.iop();
   HostSuite suite{hash};
-  const uint32_t version = RV32IM_SEAL_VERSION;
-  iop.write(&version, 1);
+  if (desc.has_version) iop.write(&desc.version, 1);
   auto commit_info = [&](const char* s) {
     uint32_t e[16];
     for (int i = 0; i < 16; i++) e[i] = fp_encode((uint32_t)(uint8_t)s[i]);
     iop.commit(suite.hash_words(e, 16));
   };
   commit_info("RISC0_STARK:v1__");
-  commit_info(RV32IM_CIRCUIT_INFO);
-  // header: globals (INVALID -> 0) followed by the raw po2 word (rv32im/src/prove/hal/mod.rs:196-206)
-  uint32_t header[RV32IM_OUTPUT_SIZE + 1];
-  for (size_t i = 0; i < RV32IM_OUTPUT_SIZE; i++) header[i] = global_host[i] == FP_INVALID ? 0u : global_host[i];
-  header[RV32IM_OUTPUT_SIZE] = po2;
-  iop.commit(suite.hash_words(header, RV32IM_OUTPUT_SIZE + 1));
-  iop.write(header, RV32IM_OUTPUT_SIZE + 1);
+  commit_info(desc.info);
+  // header: globals (INVALID -> 0) followed by the raw po2 word (rv32im/src/prove/hal/mod.rs:196-206,
+  // recursion/src/prove/mod.rs:193-206)
+  std::vector<uint32_t> header(desc.output_size + 1);
+  for (size_t i = 0; i < desc.output_size; i++) header[i] = global_host[i] == FP_INVALID ? 0u : global_host[i];
+  header[desc.output_size] = po2;
+  iop.commit(suite.hash_words(header.data(), header.size()));
+  iop.write(header.data(), header.size());
   const bool on_host = witness_on_host != 0;
   if (on_host) {
     // uploads are enqueued up front in consumption order; each group's compute waits only for its own chunks
@@ -479,10 +508,10 @@ extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po
   }
   prover.commit_group(1, on_host ? nullptr : code);
   prover.commit_group(2, on_host ? nullptr : data);
-  uint32_t mix[RV32IM_MIX_SIZE];
-  for (size_t i = 0; i < RV32IM_MIX_SIZE; i++) mix[i] = iop.random_elem();
+  std::vector<uint32_t> mix(desc.mix_size);
+  for (size_t i = 0; i < desc.mix_size; i++) mix[i] = iop.random_elem();
   prover.commit_group(0, on_host ? nullptr : accum);
-  prover.finalize(mix, header);
+  prover.finalize(mix.data(), header.data());
   R0_CUDA(cudaStreamSynchronize(ctx->stream));
   if (seal_len) *seal_len = iop.proof.size();
   R0_CHECK(seal_out_host != nullptr && iop.proof.size() <= seal_cap, "prove: seal buffer too small");
@@ -493,5 +522,26 @@ extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po
     memcpy(roots_out_host, prover.roots.data(), prover.roots.size() * 32);
   }
   if (query_pos_out_host) memcpy(query_pos_out_host, prover.query_pos.data(), prover.query_pos.size() * 4);
+}
+
+extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* code,
+                                          const uint32_t* data, const uint32_t* accum, int witness_on_host,
+                                          const uint32_t* global_host, uint32_t* seal_out_host, size_t seal_cap,
+                                          size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
+                                          uint32_t* query_pos_out_host) {
+  R0_API_BEGIN
+  prove_segment(ctx, kRv32im, hash, po2, code, data, accum, witness_on_host, global_host, seal_out_host, seal_cap, seal_len,
+                roots_out_host, roots_cap, nroots, query_pos_out_host);
+  R0_API_END
+}
+
+extern "C" r0b200_err r0b200_prove_recursion(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* ctrl,
+                                             const uint32_t* data, const uint32_t* accum, int witness_on_host,
+                                             const uint32_t* global_host, uint32_t* seal_out_host, size_t seal_cap,
+                                             size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap,
+                                             size_t* nroots, uint32_t* query_pos_out_host) {
+  R0_API_BEGIN
+  prove_segment(ctx, kRecursion, hash, po2, ctrl, data, accum, witness_on_host, global_host, seal_out_host, seal_cap,
+                seal_len, roots_out_host, roots_cap, nroots, query_pos_out_host);
   R0_API_END
 }

@@ -317,6 +317,14 @@ class B200Hal:
                                                      out.ptr, _np_ptr(_u32(poly_mix)), C.c_uint32(po2))
         check(err)
 
+    def eval_check_recursion(self, check_buf, groups, globals_, poly_mix, po2, steps):
+        """recursion circuit: groups = [accum, ctrl, data] (tap-group order), globals_ = [mix, out]"""
+        assert steps == 1 << po2 and check_buf.size() == 16 * steps
+        accum, ctrl, data = groups
+        mix, out = globals_
+        check(self._l.r0b200_eval_check_recursion(self._ctx, check_buf.ptr, ctrl.ptr, data.ptr, accum.ptr, mix.ptr,
+                                                  out.ptr, _np_ptr(_u32(poly_mix)), C.c_uint32(po2)))
+
 
 class SegmentProver:
     """Host-side mirror of `SegmentProver::prove_core`'s prove_inner block for rv32im
@@ -330,24 +338,30 @@ class SegmentProver:
         self._roots = np.zeros(8 * 16, dtype=np.uint32)
         self._qpos = np.zeros(50, dtype=np.uint32)
 
-    def prove(self, po2, code, data, accum, glob):
-        """returns (seal words, committed roots [k, 8], drawn query positions [50])"""
+    # (code/ctrl, data, accum) column counts and global words per circuit
+    SHAPES = {"rv32im": (1, 211, 103, 90), "recursion": (23, 128, 12, 32)}
+
+    def prove(self, po2, code, data, accum, glob, circuit="rv32im"):
+        """returns (seal words, committed roots [k, 8], drawn query positions [50]). circuit = "rv32im"
+        (prove_core, rv32im/src/prove/hal/mod.rs:171-222) or "recursion" (recursion/src/prove/mod.rs:179-224)"""
         hal = self.hal
         on_host = isinstance(data, np.ndarray)
         n = 1 << po2
+        c_code, c_data, c_accum, n_glob = self.SHAPES[circuit]
         if on_host:
             code, data, accum = _u32(code), _u32(data), _u32(accum)
-            assert code.size == n and data.size == 211 * n and accum.size == 103 * n
+            assert code.size == c_code * n and data.size == c_data * n and accum.size == c_accum * n
             ptrs = [_np_ptr(code), _np_ptr(data), _np_ptr(accum)]
         else:
-            assert code.size() == n and data.size() == 211 * n and accum.size() == 103 * n
+            assert code.size() == c_code * n and data.size() == c_data * n and accum.size() == c_accum * n
             ptrs = [code.ptr, data.ptr, accum.ptr]
         glob = _u32(glob)
-        assert glob.size == 90
+        assert glob.size == n_glob
         seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
-        check(hal._l.r0b200_prove_rv32im(hal._ctx, hal.hash, C.c_uint32(po2), ptrs[0], ptrs[1], ptrs[2],
-                                         C.c_int(1 if on_host else 0), _np_ptr(glob), _np_ptr(self._seal),
-                                         C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots),
-                                         C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
+        fn = hal._l.r0b200_prove_rv32im if circuit == "rv32im" else hal._l.r0b200_prove_recursion
+        check(fn(hal._ctx, hal.hash, C.c_uint32(po2), ptrs[0], ptrs[1], ptrs[2],
+                 C.c_int(1 if on_host else 0), _np_ptr(glob), _np_ptr(self._seal),
+                 C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots),
+                 C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
         return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
                 self._qpos.copy())

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "librv32im_poly_fp_ref.so")
+REF_LIB_RECURSION = os.path.join(ORACLE_DIR, "_ref", "librecursion_poly_fp_ref.so")
 
 P = 15 * 2**27 + 1
 POSEIDON2, SHA256 = 0, 1
@@ -27,7 +28,7 @@ def build(force=False):
     srcs += [os.path.join(ORACLE_DIR, "tables", f) for f in os.listdir(os.path.join(ORACLE_DIR, "tables"))]
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
-    if not os.path.exists(REF_LIB) and os.path.isdir("/root/reference"):
+    if not (os.path.exists(REF_LIB) and os.path.exists(REF_LIB_RECURSION)) and os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-j5", "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -41,7 +42,8 @@ def lib():
         _lib = C.CDLL(LIB)
         for name in ("orc_load_ref", "orc_batch_expand_into_evaluate_ntt", "orc_hash_fold", "orc_combos_divide",
                      "orc_prove_rv32im", "orc_prove_hello", "orc_verify_hello", "orc_verify_rv32im",
-                     "orc_rv32im_eval_check"):
+                     "orc_rv32im_eval_check", "orc_load_ref_recursion", "orc_recursion_eval_check",
+                     "orc_prove_recursion", "orc_verify_recursion"):
             getattr(_lib, name).restype = C.c_void_p
         for name in ("orc_fp_encode", "orc_fp_decode", "orc_fp_add", "orc_fp_sub", "orc_fp_mul", "orc_fp_pow",
                      "orc_fp_inv", "orc_rou_fwd", "orc_rou_rev", "orc_rng_elem", "orc_rng_bits"):
@@ -65,6 +67,15 @@ def have_ref():
 def load_ref():
     if not lib().orc_ref_loaded():
         _check(lib().orc_load_ref(REF_LIB.encode()))
+
+
+def have_ref_recursion():
+    return os.path.exists(REF_LIB_RECURSION)
+
+
+def load_ref_recursion():
+    if not lib().orc_ref_recursion_loaded():
+        _check(lib().orc_load_ref_recursion(REF_LIB_RECURSION.encode()))
 
 
 def ptr(a):
@@ -347,3 +358,48 @@ def synthetic_witness(po2, seed=None):
     accum = rand_elems(rng, 103 * n)
     glob = rand_elems(rng, 90)
     return code, data, accum, glob
+
+
+# ---------------------------------------------------------------- recursion circuit (ctrl 23, data 128, accum 12 columns)
+REC_COLS = dict(accum=12, ctrl=23, data=128)
+
+
+def recursion_eval_check(ctrl, data, accum, mix, glob, poly_mix, po2, begin=0, end=None):
+    load_ref_recursion()
+    domain = 4 << po2
+    if end is None:
+        end = domain
+    check = np.zeros(4 * domain, dtype=np.uint32)
+    _check(lib().orc_recursion_eval_check(ptr(check), ptr(u32(ctrl)), ptr(u32(data)), ptr(u32(accum)), ptr(u32(mix)),
+                                          ptr(u32(glob)), ptr(u32(poly_mix)), C.c_uint32(po2), _u64(begin), _u64(end)))
+    return check
+
+
+def prove_recursion(po2, ctrl, data, accum, glob, kind=POSEIDON2):
+    load_ref_recursion()
+    cap = 1 << 20
+    seal = np.zeros(cap, dtype=np.uint32)
+    roots = np.zeros(8 * 16, dtype=np.uint32)
+    qpos = np.zeros(50, dtype=np.uint32)
+    n, nr = _u64(0), _u64(0)
+    _check(lib().orc_prove_recursion(kind, C.c_uint32(po2), ptr(u32(ctrl)), ptr(u32(data)), ptr(u32(accum)),
+                                     ptr(u32(glob)), ptr(seal), _u64(cap), C.byref(n), ptr(roots), _u64(16), C.byref(nr),
+                                     ptr(qpos)))
+    return seal[:n.value].copy(), roots[:8 * nr.value].reshape(-1, 8).copy(), qpos
+
+
+def verify_recursion(seal, kind=POSEIDON2):
+    seal = u32(seal)
+    roots = np.zeros(8 * 16, dtype=np.uint32)
+    nr = _u64(0)
+    _check(lib().orc_verify_recursion(kind, ptr(seal), _u64(len(seal)), ptr(roots), C.byref(nr)))
+    return roots[:8 * nr.value].reshape(-1, 8).copy()
+
+
+def synthetic_witness_recursion(po2, seed=None):
+    """same generator as synthetic_witness, recursion shapes; the control columns are random too (the prover never
+    checks constraint satisfaction)"""
+    seed = 0x5EED1000 + po2 if seed is None else seed
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = 1 << po2
+    return rand_elems(rng, 23 * n), rand_elems(rng, 128 * n), rand_elems(rng, 12 * n), rand_elems(rng, 32)

@@ -43,7 +43,13 @@ CIRCUITS = {
         srcs=["/root/reference/risc0/circuit/rv32im-sys/kernels/cxx/rust_poly_fp_%d.cpp" % i for i in range(4)],
         arg_names=("accum", "data", "global", "mix"),
         cols=dict(accum=103, data=211, code=1),
-        n_global=90, n_mix=36,
+        n_global=90, n_mix=36, parts=8,
+    ),
+    "recursion": dict(
+        srcs=["/root/reference/risc0/circuit/recursion-sys/kernels/cxx/poly_fp.cpp"],
+        arg_names=("code", "global", "data", "mix", "accum"),   # recursion-sys/kernels/cxx/ffi.cpp:224-230
+        cols=dict(accum=12, data=128, code=23),
+        n_global=32, n_mix=20, parts=4,
     ),
 }
 
@@ -769,7 +775,7 @@ class Ptx:
         L.append(".address_size 64")
         L.append("")
         L.append(".visible .entry %s(" % self.name)
-        L.append("    .param .u64 p_check, .param .u64 p_accum, .param .u64 p_data, .param .u32 p_domain, .param .u32 p_first,")
+        L.append("    .param .u64 p_check, .param .u64 p_accum, .param .u64 p_code, .param .u64 p_data, .param .u32 p_domain, .param .u32 p_first,")
         L.append("    .param .align 16 .b8 p_cst[%d])" % self.lay.size)
         L.append(".maxntid %d, 1, 1" % threads)
         if os.environ.get("EVAL_MAXNREG"):
@@ -783,16 +789,18 @@ class Ptx:
         L.append("    .reg .u64 %%w<%d>;" % (self.nw + 40))
         L.append("    .reg .u32 %i, %domain, %mask, %first, %stride, %bdim, %bidx, %lane;")
         L.append("    .reg .u32 %o<8>, %q<8>, %iy<6>, %res<4>;")
-        L.append("    .reg .u64 %check, %accum, %data, %oaddr<4>, %off;")
+        L.append("    .reg .u64 %check, %accum, %code, %data, %oaddr<4>, %off;")
         for (buf, back), base in sorted(self.bases.items()):
             L.append("    .reg .u64 %s;" % base)
         L.append("    ld.param.u64 %check, [p_check];")
         L.append("    ld.param.u64 %accum, [p_accum];")
+        L.append("    ld.param.u64 %code, [p_code];")
         L.append("    ld.param.u64 %data, [p_data];")
         L.append("    ld.param.u32 %domain, [p_domain];")
         L.append("    ld.param.u32 %first, [p_first];")
         L.append("    cvta.to.global.u64 %check, %check;")
         L.append("    cvta.to.global.u64 %accum, %accum;")
+        L.append("    cvta.to.global.u64 %code, %code;")
         L.append("    cvta.to.global.u64 %data, %data;")
         L.append("    mov.u32 %bdim, %ntid.x;")
         L.append("    mov.u32 %bidx, %ctaid.x;")
@@ -909,10 +917,10 @@ void load_kernels() {
 }
 }  // namespace
 
-// check: 4 x domain words out. accum/data: evaluated groups (cols x domain), device. global_host: %(n_global)d words,
+// check: 4 x domain words out. accum/code/data: evaluated groups (cols x domain), device. global_host: %(n_global)d words,
 // mix_host: %(n_mix)d words (host). poly_mix: the drawn FpExt. po2 = log2(cycles); domain = 4 << po2.
-void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, const uint32_t* data, const uint32_t* global_host,
-                         const uint32_t* mix_host, const FpExt& poly_mix, uint32_t po2) {
+void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, const uint32_t* code, const uint32_t* data,
+                         const uint32_t* global_host, const uint32_t* mix_host, const FpExt& poly_mix, uint32_t po2) {
   const size_t domain = size_t(4) << po2;
   R0_CHECK(po2 + 2 <= 27 && domain <= 0x80000000ull, "eval_check: po2 out of range");
   std::call_once(g_once, load_kernels);
@@ -955,7 +963,7 @@ void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, cons
   uint32_t domain32 = (uint32_t)domain;
   for (int j = 0; j < kParts; j++) {
     uint32_t first = j == 0 ? 1u : 0u;
-    void* args[] = {&check, &accum, &data, &domain32, &first, &k};
+    void* args[] = {&check, &accum, &code, &data, &domain32, &first, &k};
     PhaseScope part(c, kPartNames[j]);
     R0_CUDA(cudaLaunchKernel((const void*)g_kernels[j], dim3(blocks), dim3(threads), args, 0, c->stream));
     count_launch(c);
@@ -966,13 +974,14 @@ void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, cons
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "rv32im"
-    nparts, flatten, threads = int(os.environ.get("EVAL_PARTS", "8")), True, int(os.environ.get("EVAL_THREADS", "128"))
+    nparts, flatten, threads = 0, True, int(os.environ.get("EVAL_THREADS", "128"))
     for a in sys.argv:
         if a.startswith("--parts="):
             nparts = int(a.split("=")[1])
         if a == "--no-flatten":
             flatten = False
     cfg = CIRCUITS[name]
+    nparts = nparts or int(os.environ.get("EVAL_PARTS", "0")) or cfg["parts"]
     ir_path = os.path.join(ROOT, "risc0_b200", "circuits", name + ".ir.json.gz")
     if "--from-ir" in sys.argv or not os.path.exists(cfg["srcs"][0]):
         dag = load_ir(ir_path)
