@@ -139,24 +139,115 @@ def node_cost(dag, x):
     return 16 if (k[0] == "*" and dag.types[k[1]] == EXT and dag.types[k[2]] == EXT) else 4
 
 
-def partition(dag, uses, nparts):
-    """split the top-level sum into `nparts` groups of terms with balanced cost; sub-expressions shared between
-    groups are recomputed in each (about a quarter of the work for 75 single-term groups, less when binned)."""
-    terms = flatten_sum(dag, uses)
+def reach_cost(dag, roots):
+    return sum(node_cost(dag, x) for x in reach(dag, roots))
+
+
+def signed_leaves(dag, uses, n):
+    """n as a signed sum of ext values if it is a single-use +/- tree: [(sign, node)] in the tree's own order"""
+    out, st = [], [(1, n, True)]
+    while st:
+        sg, x, is_root = st.pop()
+        k = dag.nodes[x]
+        if k[0] in "+-" and (is_root or uses[x] == 1) and dag.types[x] == EXT and dag.types[k[1]] == EXT and \
+                dag.types[k[2]] == EXT:
+            st.append((sg if k[0] == "+" else -sg, k[2], False))
+            st.append((sg, k[1], False))
+        else:
+            out.append((sg, x))
+    return out
+
+
+def make_sum(dag, uses, leaves):
+    """append nodes for sum(sign * leaf) to the DAG and return the id of the result"""
+    def add(key, ty):
+        dag.nodes.append(key)
+        dag.types.append(ty)
+        uses.append(1)
+        return len(dag.nodes) - 1
+    leaves = sorted(leaves, key=lambda sl: -sl[0])   # a positive leaf first when there is one (stable otherwise)
+    sg, acc = leaves[0]
+    if sg < 0:
+        acc = add(("-", add(("ce", 0, 0, 0, 0), EXT), acc), EXT)
+    for sg, x in leaves[1:]:
+        acc = add(("+" if sg > 0 else "-", acc, x), EXT)
+    return acc
+
+
+def split_units(dag, uses, limit):
+    """The constraint polynomial as a list of independent units (factors, node), each meaning prod(factors) * node,
+    whose sum is the root. Units above `limit` cost are split by distributing products over single-use sums:
+    a * (b1 + ... + bn) -> a * (b1 + .. + bk) + a * (bk+1 + ...), recomputing the (light) factor in each piece.
+    Small kernels matter: measured issue efficiency is ~50 % for 6-10 k-instruction kernels and ~20-25 % for
+    20-40 k-instruction ones (gpurun_out/evalcheck_variants7.log)."""
+    units = [((), t) for sg, t in signed_leaves(dag, uses, dag.root)]
+    assert all(sg > 0 for sg, _ in signed_leaves(dag, uses, dag.root))
+    done = []
+    while units:
+        factors, node = units.pop()
+        cost = reach_cost(dag, list(factors) + [node])
+        if cost <= limit or len(factors) > 6:
+            done.append((factors, node))
+            continue
+        k = dag.nodes[node]
+        leaves = signed_leaves(dag, uses, node)
+        if len(leaves) > 1:
+            # pack consecutive leaves into chunks under the limit
+            chunks, cur = [], []
+            for sl in leaves:
+                trial = cur + [sl]
+                if cur and reach_cost(dag, list(factors) + [x for _, x in trial]) > limit:
+                    chunks.append(cur)
+                    cur = [sl]
+                else:
+                    cur = trial
+            chunks.append(cur)
+            if len(chunks) == 1:      # a single leaf is over the limit on its own: descend into it
+                big = max(leaves, key=lambda sl: reach_cost(dag, [sl[1]]))
+                rest = [sl for sl in leaves if sl is not big]
+                pieces = [[big]] + ([rest] if rest else [])
+            else:
+                pieces = chunks
+            if len(pieces) == 1 and len(pieces[0]) == 1 and pieces[0][0][0] > 0:
+                node = pieces[0][0][1]
+                k = dag.nodes[node]
+            else:
+                for piece in pieces:
+                    if len(piece) == 1 and piece[0][0] > 0:
+                        units.append((factors, piece[0][1]))
+                    else:
+                        units.append((factors, make_sum(dag, uses, piece)))
+                continue
+        if k[0] == "*" and dag.types[node] == EXT and (uses[node] <= 1 or not factors):
+            a, b = k[1], k[2]
+            heavy, light = (a, b) if reach_cost(dag, [a]) >= reach_cost(dag, [b]) else (b, a)
+            units.append((factors + (light,), heavy))
+            continue
+        done.append((factors, node))      # cannot be split further
+    return done
+
+
+def partition(dag, uses, nparts, limit=None):
+    """groups of units with balanced cost; sub-expressions shared between groups are recomputed in each"""
+    limit = limit or int(os.environ.get("EVAL_UNIT_LIMIT", "3000"))
+    units = split_units(dag, uses, limit)
     info = []
-    for t in terms:
-        r = reach(dag, [t])
-        info.append((sum(node_cost(dag, x) for x in r), t, r))
+    for u in units:
+        r = reach(dag, list(u[0]) + [u[1]])
+        info.append((sum(node_cost(dag, x) for x in r), u, r))
+    total = sum(c for c, _, _ in info)
+    if not nparts:
+        nparts = max(1, (total + limit - 1) // limit)
     info.sort(key=lambda z: -z[0])
     bins = [dict(terms=[], nodes=set(), cost=0) for _ in range(nparts)]
-    for c, t, r in info:
+    for c, u, r in info:
         best, best_cost = None, None
         for b in bins:
             extra = sum(node_cost(dag, x) for x in r - b["nodes"])
             tot = b["cost"] + extra
             if best is None or tot < best_cost:
                 best, best_cost = b, tot
-        best["terms"].append(t)
+        best["terms"].append(u)
         best["cost"] = best_cost
         best["nodes"] |= r
     return [b for b in bins if b["terms"]]
@@ -374,11 +465,24 @@ def lower(dag, terms, lay):
             stack.pop()
         return memo[n]
 
+    def as_ext(v):
+        return v if isinstance(v, tuple) else (v, zero, zero, zero)
+
     tot = [zero] * 4
-    for t in terms:
-        v = get(t)
-        if not isinstance(v, tuple):
-            v = (v, zero, zero, zero)
+    for unit in terms:
+        factors, node = unit if isinstance(unit, tuple) else ((), unit)
+        v = get(node)
+        for f in factors:
+            fv = get(f)
+            if isinstance(v, tuple) and isinstance(fv, tuple):
+                v = ext_mul(fv, v)
+            elif isinstance(v, tuple):
+                v = tuple(S.mul(v[c], fv) for c in range(4))
+            elif isinstance(fv, tuple):
+                v = tuple(S.mul(fv[c], v) for c in range(4))
+            else:
+                v = S.mul(fv, v)
+        v = as_ext(v)
         tot = [S.add(tot[c], v[c]) for c in range(4)]
     return S, tot
 
@@ -981,7 +1085,7 @@ def main():
         if a == "--no-flatten":
             flatten = False
     cfg = CIRCUITS[name]
-    nparts = nparts or int(os.environ.get("EVAL_PARTS", "0")) or cfg["parts"]
+    nparts = nparts or int(os.environ.get("EVAL_PARTS", "0"))   # 0: as many parts as the unit limit asks for
     ir_path = os.path.join(ROOT, "risc0_b200", "circuits", name + ".ir.json.gz")
     if "--from-ir" in sys.argv or not os.path.exists(cfg["srcs"][0]):
         dag = load_ir(ir_path)
