@@ -23,21 +23,44 @@ constexpr uint32_t FP_INVALID = 0xFFFFFFFFu;
 
 R0_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
+// On sm_100a the fma pipe issues an IMAD every cycle per SM sub-partition while the alu pipe (IADD3, VIADDMNMX, LOP3)
+// takes two (ncu: profiles/r1_ncu_full_summaries.md, hash_rows). Plain 32-bit adds in the hot kernels are therefore
+// written as x * 1 + y with the 1 (or -1) read from the constant bank, which the compiler cannot fold: they become
+// IMADs, and only the final "conditional subtract" (one fused VIADDMNMX) stays on the alu pipe.
+#if defined(__CUDA_ARCH__)
+__constant__ uint32_t r0_fma_one = 1u;
+__constant__ uint32_t r0_fma_neg1 = 0xFFFFFFFFu;
+#define R0_ADD32(a, b) ((a) * r0_fma_one + (b))
+#define R0_SUB32(a, b) ((b) * r0_fma_neg1 + (a))
+#else
+#define R0_ADD32(a, b) ((a) + (b))
+#define R0_SUB32(a, b) ((a) - (b))
+#endif
+
 R0_HD uint32_t fp_add(uint32_t a, uint32_t b) {
-  uint32_t r = a + b;
+  uint32_t r = R0_ADD32(a, b);
   return umin32(r, r - P);
 }
 R0_HD uint32_t fp_sub(uint32_t a, uint32_t b) {
-  uint32_t r = a - b;
+  uint32_t r = R0_SUB32(a, b);
   return umin32(r, r + P);
 }
 R0_HD uint32_t fp_neg(uint32_t a) { return fp_sub(0u, a); }
-// Montgomery reduction of t < 2^32 * P : returns t / 2^32 mod P, canonical
+// Montgomery reduction of t < 2^32 * P : returns t / 2^32 mod P, canonical.
+// Subtractive form: m = lo(t) * P^-1, so lo(m * P) == lo(t) and t - m*P = 2^32 * (hi(t) - hi(m*P)) exactly - no carry
+// to propagate. hi(t) < P and hi(m*P) < P, so the difference is in (-P, P); the wrapped-unsigned "min(r, r + P)" maps it
+// to [0, P). On sm_100a this is IMAD, IMAD.HI.U32, IADD3, VIADDMNMX.U32 (the additive form t + (-m)*P needs the
+// carry out of the low word on top).
+constexpr uint32_t MONT_PINV = 0x88000001u;  // P^-1 mod 2^32
 R0_HD uint32_t mont_reduce(uint64_t t) {
-  uint32_t m = (uint32_t)t * MONT_NINV;
-  uint64_t u = t + (uint64_t)m * P;
-  uint32_t r = (uint32_t)(u >> 32);
-  return umin32(r, r - P);
+  const uint32_t m = (uint32_t)t * MONT_PINV;
+#if defined(__CUDA_ARCH__)
+  const uint32_t h = __umulhi(m, P);
+#else
+  const uint32_t h = (uint32_t)(((uint64_t)m * P) >> 32);
+#endif
+  const uint32_t r = R0_SUB32((uint32_t)(t >> 32), h);
+  return umin32(r, r + P);
 }
 R0_HD uint32_t fp_mul(uint32_t a, uint32_t b) { return mont_reduce((uint64_t)a * b); }
 R0_HD uint32_t fp_encode(uint32_t x) { return fp_mul(MONT_R2, x % P); }

@@ -283,6 +283,7 @@ def schedule_part(dag, terms):
 
 # ------------------------------------------------------------------------------------------------ scalar lowering
 NINV = 0x77FFFFFF            # -P^-1 mod 2^32
+PINV = 0x88000001            # P^-1 mod 2^32
 MONT_ONE = R
 RINV = pow(R, -1, P)
 NBETA_M = mont(P - 11)
@@ -689,15 +690,15 @@ class Ptx:
         return acc2, lim - 1
 
     def mont_finish(self, dst, acc):
-        lo, hi, m, hi2, x = self.t(), self.t(), self.t(), self.t(), self.t()
-        w2 = self.w()
-        self.emit("cvt.u32.u64 %s, %s;" % (lo, acc))
-        self.emit("mul.lo.u32 %s, %s, %d;" % (m, lo, NINV))
-        self.emit("mad.wide.u32 %s, %s, %d, %s;" % (w2, m, P, acc))
-        self.emit("mov.b64 {%s, %s}, %s;" % (x, hi2, w2))
-        hi3 = self.t()
-        self.emit("add.u32 %s, %s, %d;" % (hi3, hi2, (1 << 32) - P))
-        self.emit("min.u32 %s, %s, %s;" % (dst, hi2, hi3))
+        # subtractive Montgomery reduction (csrc/fp.cuh mont_reduce): m = lo * P^-1; r = hi - hi(m * P) in (-P, P);
+        # canonical = min.u32(r, r + P). No carry chain, 4 instructions.
+        lo, hi, m, h, r, r2 = self.t(), self.t(), self.t(), self.t(), self.t(), self.t()
+        self.emit("mov.b64 {%s, %s}, %s;" % (lo, hi, acc))
+        self.emit("mul.lo.u32 %s, %s, %d;" % (m, lo, PINV))
+        self.emit("mul.hi.u32 %s, %s, %d;" % (h, m, P))
+        self.emit("sub.u32 %s, %s, %s;" % (r, hi, h))
+        self.emit("add.u32 %s, %s, %d;" % (r2, r, P))
+        self.emit("min.u32 %s, %s, %s;" % (dst, r, r2))
 
     def node(self, i):
         S = self.S
