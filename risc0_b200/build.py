@@ -114,6 +114,8 @@ def build(force=False, verbose=False, jobs=None):
         cubins.append(cubin)
         if force or not os.path.exists(cubin) or os.path.getmtime(cubin) < os.path.getmtime(ptx):
             ptx_todo.append((ptx, cubin))
+    if (todo or ptx_todo) and os.path.exists(LIB):
+        os.remove(LIB)   # never leave a stale library behind a failed rebuild
     if todo or ptx_todo:
         with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
             futs = [ex.submit(_compile, s_, o_, verbose) for s_, o_ in todo]

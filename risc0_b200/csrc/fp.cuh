@@ -23,19 +23,12 @@ constexpr uint32_t FP_INVALID = 0xFFFFFFFFu;
 
 R0_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-// On sm_100a the fma pipe issues an IMAD every cycle per SM sub-partition while the alu pipe (IADD3, VIADDMNMX, LOP3)
-// takes two (ncu: profiles/r1_ncu_full_summaries.md, hash_rows). Plain 32-bit adds in the hot kernels are therefore
-// written as x * 1 + y with the 1 (or -1) read from the constant bank, which the compiler cannot fold: they become
-// IMADs, and only the final "conditional subtract" (one fused VIADDMNMX) stays on the alu pipe.
-#if defined(__CUDA_ARCH__)
-__constant__ uint32_t r0_fma_one = 1u;
-__constant__ uint32_t r0_fma_neg1 = 0xFFFFFFFFu;
-#define R0_ADD32(a, b) ((a) * r0_fma_one + (b))
-#define R0_SUB32(a, b) ((b) * r0_fma_neg1 + (a))
-#else
+// Note on pipes (sm_100a, ncu in profiles/): IMAD-class instructions issue on the fma pipe, IADD3 / VIADDMNMX / LOP3 on
+// the alu pipe. Kernels whose mix is alu-heavy (Poseidon2's linear layers) move some plain adds to the fma pipe by
+// writing them as x * 1 + y with an opaque 1 (poseidon2.cu); doing that for EVERY add over-loads the fma pipe and is
+// slower (measured: hash_rows 2.01 -> 1.68 Gperm/s), so the generic helpers below stay plain.
 #define R0_ADD32(a, b) ((a) + (b))
 #define R0_SUB32(a, b) ((a) - (b))
-#endif
 
 R0_HD uint32_t fp_add(uint32_t a, uint32_t b) {
   uint32_t r = R0_ADD32(a, b);

@@ -23,7 +23,10 @@ __constant__ uint32_t c_one;  // = 1, opaque to the compiler: a * c_one + b is a
 
 // The permutation is bound by the alu pipe (every modular add / product ends in a VIADDMNMX there), while the fma pipe
 // is half idle; adds in the linear layer are therefore issued as IMAD (x * 1 + y) to balance the two pipes.
-__device__ __forceinline__ uint32_t fp_add_fma(uint32_t a, uint32_t b) { return fp_add(a, b); }
+__device__ __forceinline__ uint32_t fp_add_fma(uint32_t a, uint32_t b) {
+  uint32_t r = a * c_one + b;
+  return umin32(r, r - P);
+}
 
 __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
   uint32_t x2 = fp_mul(x, x);
