@@ -144,3 +144,15 @@ def test_prove_segment_po2_20_properties(hal):
     vroots = O.verify_rv32im(seal)
     assert np.array_equal(vroots, roots)
     assert int(qpos.max()) < (4 << po2)
+
+
+@pytest.mark.parametrize("po2", [21, 22])
+def test_prove_segment_max_sizes_properties(hal, po2):
+    # DEFAULT_MAX_PO2 = 22 (BASELINE config 3 segment size): 4N = 2^24-point NTTs, 211 x 2^24 evaluations (14 GB), indices
+    # beyond 2^32 words. Checked through the seal-size formula and the restated verifier (all Merkle paths, FRI folds
+    # and DEEP quotients of the 50 queries), as at po2 = 20.
+    code, data, accum, glob = O.synthetic_witness(po2)
+    seal, roots, qpos = SegmentProver(hal).prove(po2, code, data, accum, glob)
+    assert len(seal) == seal_words(po2)
+    vroots = O.verify_rv32im(seal)
+    assert np.array_equal(vroots, roots)
