@@ -670,30 +670,36 @@ class Ptx:
             self.body.append("    bar.sync 0;" if self.use_bar else "    @%p0 bra DONE;")
             self.last_fence = self.pos
 
-    def reduce_hi(self, acc, bound):
-        """bring a 64-bit accumulator (value <= bound) under P * 2^32; returns (acc', bound')"""
+    def fold_hi(self, hi, bound):
+        """bring a 64-bit accumulator (lo, hi) with value <= bound under P * 2^32 by reducing its high word in place;
+        returns the new bound"""
         lim = P << 32
         if bound < lim:
-            return acc, bound
-        lo, hi = self.t(), self.t()
-        self.emit("mov.b64 {%s, %s}, %s;" % (lo, hi, acc))
+            return bound
         if bound >= 2 * lim:
-            h2, h3 = self.t(), self.t()
+            h2 = self.t()
             self.emit("add.u32 %s, %s, %d;" % (h2, hi, (1 << 32) - 2 * P))
-            self.emit("min.u32 %s, %s, %s;" % (h3, hi, h2))
-            hi = h3
-        h4, h5 = self.t(), self.t()
+            self.emit("min.u32 %s, %s, %s;" % (hi, hi, h2))
+        h4 = self.t()
         self.emit("add.u32 %s, %s, %d;" % (h4, hi, (1 << 32) - P))
-        self.emit("min.u32 %s, %s, %s;" % (h5, hi, h4))
-        acc2 = self.w()
-        self.emit("mov.b64 %s, {%s, %s};" % (acc2, lo, h5))
-        return acc2, lim - 1
+        self.emit("min.u32 %s, %s, %s;" % (hi, hi, h4))
+        return lim - 1
 
-    def mont_finish(self, dst, acc):
+    def mac(self, lo, hi, a, b, first):
+        """(lo, hi) += a * b as the carry-chained 32-bit pair that ptxas folds into ONE IMAD.WIDE with a 64-bit
+        accumulator operand (a mad.wide chain is instead re-associated into IMAD.WIDE + IADD3/IADD3.X trees, which
+        puts ~1.5 extra instructions per product on the half-rate alu pipe)"""
+        if first:
+            self.emit("mul.lo.u32 %s, %s, %s;" % (lo, a, b))
+            self.emit("mul.hi.u32 %s, %s, %s;" % (hi, a, b))
+        else:
+            self.emit("mad.lo.cc.u32 %s, %s, %s, %s;" % (lo, a, b, lo))
+            self.emit("madc.hi.u32 %s, %s, %s, %s;" % (hi, a, b, hi))
+
+    def mont_finish(self, dst, lo, hi):
         # subtractive Montgomery reduction (csrc/fp.cuh mont_reduce): m = lo * P^-1; r = hi - hi(m * P) in (-P, P);
         # canonical = min.u32(r, r + P). No carry chain, 4 instructions.
-        lo, hi, m, h, r, r2 = self.t(), self.t(), self.t(), self.t(), self.t(), self.t()
-        self.emit("mov.b64 {%s, %s}, %s;" % (lo, hi, acc))
+        m, h, r, r2 = self.t(), self.t(), self.t(), self.t()
         self.emit("mul.lo.u32 %s, %s, %d;" % (m, lo, PINV))
         self.emit("mul.hi.u32 %s, %s, %d;" % (h, m, P))
         self.emit("sub.u32 %s, %s, %s;" % (r, hi, h))
@@ -731,12 +737,12 @@ class Ptx:
         elif o == "N":
             self.emit("sub.u32 %s, %d, %s;" % (dst, P, self.use(k[1])))
         elif o == "*":
-            acc = self.w()
+            lo, hi = self.t(), self.t()
             a, b = k[1], k[2]
             if S.nodes[a][0] == "i":
                 a, b = b, a
-            self.emit("mul.wide.u32 %s, %s, %s;" % (acc, self.use(a), self.use(b)))
-            self.mont_finish(dst, acc)
+            self.mac(lo, hi, self.use(a), self.use(b), True)
+            self.mont_finish(dst, lo, hi)
         else:
             raise ValueError(k)
 
@@ -841,7 +847,7 @@ class Ptx:
                     a, b = b, a
                 key = tuple(sorted(x for x in (a, b) if not self.is_const(x)))
                 keyed.setdefault(key, []).append((d, a, b))
-        acc = {d: None for d in dots}
+        acc = {d: None for d in dots}      # (lo, hi) register pair once the first product has been issued
         bound = {d: 0 for d in dots}
         if os.environ.get("EVAL_ORDER", "program") == "weight":
             order = sorted(keyed, key=lambda key: -max([self.weight[x] for x in key] or [0]))
@@ -855,16 +861,17 @@ class Ptx:
                     self.ensure(x)      # constants: ld.param emitted on first use
                 pb = self.bound(a) * self.bound(b)
                 if acc[d] is not None and bound[d] + pb >= (1 << 64):
-                    acc[d], bound[d] = self.reduce_hi(acc[d], bound[d])
-                nacc = self.w()
+                    bound[d] = self.fold_hi(acc[d][1], bound[d])
+                ua, ub = self.use(a), self.use(b)
                 if acc[d] is None:
-                    self.emit("mul.wide.u32 %s, %s, %s;" % (nacc, self.use(a), self.use(b)))
+                    acc[d] = (self.t(), self.t())
+                    self.mac(acc[d][0], acc[d][1], ua, ub, True)
                 else:
-                    self.emit("mad.wide.u32 %s, %s, %s, %s;" % (nacc, self.use(a), self.use(b), acc[d]))
-                acc[d], bound[d] = nacc, bound[d] + pb
+                    self.mac(acc[d][0], acc[d][1], ua, ub, False)
+                bound[d] += pb
         for d in dots:
-            a, bnd = self.reduce_hi(acc[d], bound[d])
-            self.mont_finish("%%v%d" % d, a)
+            self.fold_hi(acc[d][1], bound[d])
+            self.mont_finish("%%v%d" % d, acc[d][0], acc[d][1])
             self.done.add(d)
         self.fence()
 
@@ -938,9 +945,9 @@ class Ptx:
         L.append("    selp.u32 %iy4, %iy3, %iy4, %p2;")
         self.body = []
         for c in range(4):
-            acc = self.w()
-            self.emit("mul.wide.u32 %s, %s, %%iy4;" % (acc, self.use(outs[c]) if self.S.nodes[outs[c]][0] != "i" else self._mat(outs[c])))
-            self.mont_finish("%%res%d" % c, acc)
+            lo, hi = self.t(), self.t()
+            self.mac(lo, hi, self.use(outs[c]) if self.S.nodes[outs[c]][0] != "i" else self._mat(outs[c]), "%iy4", True)
+            self.mont_finish("%%res%d" % c, lo, hi)
         L.extend(self.body)
         L.append("    mul.wide.u32 %off, %i, 4;")
         L.append("    add.u64 %oaddr0, %check, %off;")
