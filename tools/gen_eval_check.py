@@ -630,7 +630,7 @@ class Ptx:
         self.pos = 0
         self.remat = int(os.environ.get("EVAL_REMAT_DIST", "400"))   # re-load / recompute instead of keeping alive
         self.remat_cost = int(os.environ.get("EVAL_REMAT_COST", "8"))
-        self.split = int(os.environ.get("EVAL_SPLIT", "400"))
+        self.split = int(os.environ.get("EVAL_SPLIT", "1600"))
         self.last_fence = 0
         self.use_bar = os.environ.get("EVAL_BAR", "0") == "1"
         self.bases = {}
