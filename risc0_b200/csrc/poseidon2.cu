@@ -28,11 +28,22 @@ __device__ __forceinline__ uint32_t fp_add_fma(uint32_t a, uint32_t b) {
   return umin32(r, r - P);
 }
 
+// Signed Montgomery product: for |a|, |b| < P the result is in (-P, P) and congruent to a*b/2^32 - exact because the
+// low words of t and m*P cancel. Inside the x^7 chain the intermediate powers never meet an addition, so they can stay
+// in this non-canonical signed form and only x^7 pays the "conditional add P" (one VIADDMNMX instead of four on the
+// alu pipe, which is the pipe that bounds the permutation).
+__device__ __forceinline__ int32_t mul_signed(int32_t a, int32_t b) {
+  const int64_t t = (int64_t)a * b;
+  const int32_t m = (int32_t)((uint32_t)t * MONT_PINV);
+  return (int32_t)(t >> 32) - __mulhi(m, (int32_t)P);
+}
 __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
-  uint32_t x2 = fp_mul(x, x);
-  uint32_t x4 = fp_mul(x2, x2);
-  uint32_t x6 = fp_mul(x4, x2);
-  return fp_mul(x6, x);
+  const int32_t x1 = (int32_t)x;
+  const int32_t x2 = mul_signed(x1, x1);
+  const int32_t x4 = mul_signed(x2, x2);
+  const int32_t x6 = mul_signed(x4, x2);
+  const uint32_t r = (uint32_t)mul_signed(x6, x1);
+  return umin32(r, r + P);
 }
 __device__ __forceinline__ uint32_t dbl(uint32_t x) { return fp_add(x, x); }
 __device__ __forceinline__ uint32_t dbl_fma(uint32_t x) { return fp_add_fma(x, x); }
