@@ -19,6 +19,8 @@ namespace r0 {
 __constant__ uint32_t c_rc_full[8 * 24];
 __constant__ uint32_t c_rc_partial[21];
 __constant__ uint32_t c_diag[24];
+__constant__ uint32_t c_diag_n[24];   // M_INT_DIAG_HZN in NORMAL form: x~ * d mod P keeps x~'s Montgomery form
+__constant__ uint32_t c_diag_q[24];   // floor(d * 2^32 / P): Shoup's precomputed quotient for multiplying by the constant d
 __constant__ uint32_t c_one;  // = 1, opaque to the compiler: a * c_one + b is an IMAD, i.e. an add on the fma pipe
 
 // The permutation is bound by the alu pipe (every modular add / product ends in a VIADDMNMX there), while the fma pipe
@@ -95,11 +97,16 @@ __device__ __forceinline__ void partial_round(uint32_t (&c)[24], int r) {
 #pragma unroll
   for (int i = 0; i < 6; i++) p[i] = fp_add_fma(p[2 * i], p[2 * i + 1]);
   uint32_t sum = fp_add_fma(fp_add_fma(fp_add_fma(p[0], p[1]), fp_add_fma(p[2], p[3])), fp_add_fma(p[4], p[5]));
-  // sum + diag_i * c_i as one Montgomery reduction: sum enters the 64-bit product as sum * 2^32 mod P (MONT_ONE), so the
-  // total stays below P * 2^32 and the separate modular add disappears
-  const uint64_t s64 = (uint64_t)sum * MONT_ONE;
+  // sum + diag_i * c_i. diag_i is a constant, so Shoup's method applies: q = hi(c * floor(d 2^32 / P)), r = c*d - q*P in
+  // [0, 2P) using only the LOW 32 bits of both products: IMAD.HI + 2 IMAD = 8 fma-pipe cycles instead of the 10 of a
+  // Montgomery product (IMAD.WIDE and IMAD.HI issue at quarter rate on sm_100a, profiles/r1_int_pipe_rates.log).
 #pragma unroll
-  for (int i = 0; i < 24; i++) c[i] = mont_reduce((uint64_t)c_diag[i] * c[i] + s64);
+  for (int i = 0; i < 24; i++) {
+    const uint32_t q = __umulhi(c[i], c_diag_q[i]);
+    uint32_t r = c[i] * c_diag_n[i] - q * P;
+    r = umin32(r, r - P);
+    c[i] = fp_add(r, sum);
+  }
 }
 
 __device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) {
@@ -212,6 +219,10 @@ void r0_poseidon2_init(Ctx* c) {
                                   cudaMemcpyHostToDevice, c->stream));
   R0_CUDA(cudaMemcpyToSymbolAsync(c_diag, R0_P2_DIAG_MONT, sizeof(R0_P2_DIAG_MONT), 0, cudaMemcpyHostToDevice,
                                   c->stream));
+  uint32_t dq[24];
+  for (int i = 0; i < 24; i++) dq[i] = (uint32_t)(((uint64_t)R0_P2_DIAG[i] << 32) / P);
+  R0_CUDA(cudaMemcpyToSymbolAsync(c_diag_n, R0_P2_DIAG, sizeof(R0_P2_DIAG), 0, cudaMemcpyHostToDevice, c->stream));
+  R0_CUDA(cudaMemcpyToSymbolAsync(c_diag_q, dq, sizeof(dq), 0, cudaMemcpyHostToDevice, c->stream));
   const uint32_t one = 1;
   R0_CUDA(cudaMemcpyToSymbolAsync(c_one, &one, sizeof(one), 0, cudaMemcpyHostToDevice, c->stream));
   R0_CUDA(cudaStreamSynchronize(c->stream));

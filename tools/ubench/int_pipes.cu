@@ -51,6 +51,23 @@ __global__ void k(uint32_t* out, uint32_t a0, uint32_t b0) {
         uint32_t r = (uint32_t)(t >> 32) - h;
         uint32_t r2 = r + 0x78000001u;
         x[i] = r < r2 ? r : r2;
+      } else if (OP == 9) {  // Montgomery product, m = lo * P^-1 as shifts + 3-input add (P^-1 = 2^31 + 2^27 + 1)
+        uint64_t t = (uint64_t)x[i] * y[i];
+        uint32_t lo = (uint32_t)t, s27, s31, m;
+        asm volatile("shl.b32 %0, %1, 27;" : "=r"(s27) : "r"(lo));
+        asm volatile("shl.b32 %0, %1, 31;" : "=r"(s31) : "r"(lo));
+        asm volatile("add.u32 %0, %1, %2;" : "=r"(m) : "r"(lo), "r"(s27));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(m) : "r"(s31));
+        uint32_t h = __umulhi(m, 0x78000001u);
+        uint32_t r = (uint32_t)(t >> 32) - h;
+        uint32_t r2 = r + 0x78000001u;
+        x[i] = r < r2 ? r : r2;
+      } else if (OP == 10) {  // SHF / shl alone
+        asm volatile("shl.b32 %0, %0, 3;" : "+r"(x[i]));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+      } else if (OP == 11) {  // LOP3
+        asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+        asm volatile("and.b32 %0, %0, 0x7fffffff;" : "+r"(x[i]));
       }
     }
   }
@@ -95,6 +112,9 @@ int main() {
   run<5>("IMAD + VIADDMNMX", 2, out, p.multiProcessorCount, ghz);
   run<6>("IADD3 + VIADDMNMX", 2, out, p.multiProcessorCount, ghz);
   run<7>("IMAD.WIDE accumulate (cc pair)", 1, out, p.multiProcessorCount, ghz);
-  run<8>("Montgomery product (5 instr)", 5, out, p.multiProcessorCount, ghz);
+  run<8>("Montgomery product (5 instr)", 1, out, p.multiProcessorCount, ghz);
+  run<9>("Montgomery product, m by shift-add", 1, out, p.multiProcessorCount, ghz);
+  run<10>("shl + add", 2, out, p.multiProcessorCount, ghz);
+  run<11>("xor + and (LOP3)", 2, out, p.multiProcessorCount, ghz);
   return 0;
 }
