@@ -5,8 +5,8 @@ expression DAG.
 
 Input (read-only, build container only):
     /root/reference/risc0/circuit/rv32im-sys/kernels/cxx/rust_poly_fp_{0..3}.cpp   (rv32im, 52.9 k lines)
-Output: a `Dag` object; `tools/gen_eval_check.py` schedules it and emits sm_100a CUDA, and also serialises it to
-`risc0_b200/circuits/*.ir.json.gz` so the generated kernel can be rebuilt without the reference tree.
+Output: a `Dag` object; `tools/gen_eval_check.py` lowers and schedules it and emits sm_100a PTX, and also serialises it
+to `risc0_b200/circuits/*.ir.json.gz` so the generated kernels can be rebuilt without the reference tree.
 
 Because BabyBear arithmetic is exact, ANY re-association / re-ordering of the DAG yields bit-identical results; the
 generator is free to restructure as long as it evaluates the same polynomial. The oracle for the result is the
@@ -202,7 +202,6 @@ def build_dag(fns, entry="poly_fp", arg_names=("accum", "data", "global", "mix")
         return env[tok]
 
     sys.setrecursionlimit(10000)
-    dag.root = run(entry, ["ARGS"]) if False else None
     # entry has signature (cycle, steps, poly_mix, Fp** args): no extra formals
     params, body = fns[entry]
     fns[entry] = (params[:3], body)

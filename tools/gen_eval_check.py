@@ -9,13 +9,19 @@ by ptxas and embedded in libr0b200.so by risc0_b200/build.py) plus the host laun
 What the kernel computes is CircuitHal::eval_check (risc0/zkp/src/hal/mod.rs:279-289; CPU spec
 risc0/circuit/rv32im/src/prove/hal/cpu.rs:145-208): for every point i of the 4N domain,
     check[k*D + i] = (poly_fp(i) * ((3 * w_4N^i)^N - 1)^-1)[k].
-How it is computed differs from both reference back ends (DESIGN.md "eval_check"):
-  * one flat DAG (common sub-expressions merged across the reference's 21 sub-functions), scheduled depth-first with
-    the heavier operand first so that live ranges stay short;
-  * every `acc + v * poly_mix[k]` chain is flattened into a sum of products and evaluated with lazy 64-bit
-    multiply-accumulate (one IMAD.WIDE per term and component, one Montgomery reduction per chain) - exact
-    arithmetic makes any re-association bit-identical;
-  * poly_mix powers (and their -11 multiples for the X^4 = -11 wrap) sit in the constant bank, so they are free operands;
+How it is computed differs from both reference back ends:
+  * one flat DAG (common sub-expressions merged across the reference's generated sub-functions), lowered to 32-bit
+    scalar field operations;
+  * the top-level sum is cut into units of bounded cost (oversized terms are split by distributing products over sums)
+    and binned into ~45 small part kernels: small straight-line kernels run at about twice the issue efficiency of
+    large ones;
+  * every `acc + v * poly_mix[k]` chain is flattened into a sum of products and evaluated as a streamed 64-bit
+    multiply-accumulate (carry-chained mad.lo.cc / madc.hi pairs that ptxas folds into single IMAD.WIDE accumulates),
+    one Montgomery reduction per sum - exact arithmetic makes any re-association bit-identical;
+  * values are emitted on demand right before first use; cheap ones and taps are recomputed / re-loaded instead of
+    being kept alive; a never-taken branch every 1600 instructions bounds ptxas' scheduling window;
+  * poly_mix powers (and their -11 multiples for the X^4 = -11 wrap), globals and mix values travel in the kernel
+    parameter block (constant bank), so they are free operands;
   * the divisor only takes 4 values ((3w^i)^N = 3^N * w_4^(i mod 4)): its inverses are computed once on the host.
 """
 import gzip
@@ -71,49 +77,7 @@ def load_ir(path):
     return dag
 
 
-# ------------------------------------------------------------------------------------------------ scheduling
-def schedule(dag):
-    """post-order DFS from the root, heavier operand first (Sethi-Ullman flavour). Returns node ids in emit order."""
-    n = len(dag.nodes)
-    weight = [1] * n
-    for i, k in enumerate(dag.nodes):  # ids are topologically ordered by construction (operands before users)
-        if k[0] in "+-*":
-            weight[i] = 1 + weight[k[1]] + weight[k[2]]
-    order, seen = [], [False] * n
-    stack = [(dag.root, False)]
-    while stack:
-        node, done = stack.pop()
-        if done:
-            order.append(node)
-            continue
-        if seen[node]:
-            continue
-        seen[node] = True
-        stack.append((node, True))
-        k = dag.nodes[node]
-        if k[0] in "+-*":
-            a, b = k[1], k[2]
-            first, second = (a, b) if weight[a] >= weight[b] else (b, a)
-            stack.append((second, False))
-            stack.append((first, False))
-    return order
-
-
-def flatten_sum(dag, uses):
-    """top-level terms of the root: root = sum(terms) (ext additions used once are folded into the sum)"""
-    terms, st = [], [dag.root]
-    while st:
-        n = st.pop()
-        k = dag.nodes[n]
-        if k[0] == "+" and dag.types[n] == EXT and dag.types[k[1]] == EXT and dag.types[k[2]] == EXT and (
-                n == dag.root or uses[n] == 1):
-            st.append(k[2])
-            st.append(k[1])
-        else:
-            terms.append(n)
-    return terms
-
-
+# ------------------------------------------------------------------------------------------------ partitioning
 def reach(dag, roots):
     seen, st = set(), list(roots)
     while st:
@@ -251,34 +215,6 @@ def partition(dag, uses, nparts, limit=None):
         best["cost"] = best_cost
         best["nodes"] |= r
     return [b for b in bins if b["terms"]]
-
-
-def schedule_part(dag, terms):
-    """like schedule() but for a set of roots; returns emit order"""
-    n = len(dag.nodes)
-    weight = [1] * n
-    for i, k in enumerate(dag.nodes):
-        if k[0] in "+-*":
-            weight[i] = 1 + weight[k[1]] + weight[k[2]]
-    order, seen = [], set()
-    for root in terms:
-        stack = [(root, False)]
-        while stack:
-            node, done = stack.pop()
-            if done:
-                order.append(node)
-                continue
-            if node in seen:
-                continue
-            seen.add(node)
-            stack.append((node, True))
-            k = dag.nodes[node]
-            if k[0] in "+-*":
-                a, b = k[1], k[2]
-                first, second = (a, b) if weight[a] >= weight[b] else (b, a)
-                stack.append((second, False))
-                stack.append((first, False))
-    return order
 
 
 # ------------------------------------------------------------------------------------------------ scalar lowering
@@ -1119,7 +1055,7 @@ def main():
         S, outs = lower(dag, part["terms"], lay)
         if flatten:
             S, outs = flatten_sums(S, outs)
-        order = schedule_scalars(S, outs)
+        order = schedule_scalars(S, outs)   # only for the statistics printed below; emission is demand-driven
         kname = "eval_check_%s_p%d" % (name, j)
         ptx = Ptx(S, kname, lay).kernel(order, outs, threads)
         with open(os.path.join(gen_dir, kname + ".ptx"), "w") as f:
