@@ -211,8 +211,13 @@ def main():
     top = max(families.items(), key=lambda kv: kv[1]["ms"])
     tname, t = top
     nlaunch = t["n"]
+    stats = {}
+    try:
+        stats = json.load(open(os.path.join(ROOT, "risc0_b200", "circuits", "rv32im.stats.json")))
+    except Exception:
+        pass
     if tname == "eval_check":
-        nlaunch = sum(v["n"] for k, v in phases.items() if k.startswith("eval_check_p"))
+        nlaunch = t["n"] * int(stats.get("parts", 1))     # every eval_check call launches all part kernels
     achieved = t["bytes"] / (t["ms"] * 1e-3) / 1e9 if t["ms"] > 0 else 0.0
     # DRAM traffic per launch from the committed ncu --set full capture of this kernel family (profiles/), scaled by
     # the number of domain points; null when no capture exists for the family
@@ -237,6 +242,18 @@ def main():
     phase_ms = {k: round(v["ms"] / args.steps, 4) for k, v in sorted(phases.items(), key=lambda kv: -kv[1]["ms"])}
     phase_gbs = {k: round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) for k, v in phases.items() if v["ms"] > 0 and v["bytes"] > 0}
 
+    # INT32 view of the same family: these kernels are bound by the fma pipe's quarter-rate wide multiplies
+    # (IMAD.WIDE / IMAD.HI: 4 cycles per warp instruction per sub-partition, IMAD: 2 - profiles/r1_int_pipe_rates.log),
+    # so the meaningful ceiling is fma-pipe cycles, not bytes
+    int32 = None
+    sm_mhz = (sampler.result().get("sm_mhz") or 1965.0)
+    smsp_cycles = 148 * 4 * sm_mhz * 1e6 * (t["ms"] * 1e-3)       # available sub-partition cycles during the family's time
+    if tname == "eval_check" and stats:
+        per_point = 4.0 * stats["wide_multiplies"] + 6.0 * stats["reductions"]
+        need = per_point * (4 << po2) / 32.0 * t["n"]
+        int32 = {"bound": "fma pipe (IMAD.WIDE 4 clk, IMAD 2 clk, IMAD.HI 4 clk per warp instruction per sub-partition)",
+                 "wide_multiplies_per_point": stats["wide_multiplies"], "reductions_per_point": stats["reductions"],
+                 "fma_cycles_needed": need, "smsp_cycles_available": smsp_cycles, "frac": need / smsp_cycles}
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
@@ -262,7 +279,7 @@ def main():
                            "parallelism": "segments sharded one per GPU, no collective"},
                 "e2e": {"value": e2e_value, "unit": "cycles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(seal.nbytes),
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "gpu_launches": int(launches), "roofline": roofline, "int32_roofline": int32, "cpu_baseline": cpu_baseline,
                 "phase_ms_per_step": phase_ms, "phase_alg_GBps": phase_gbs, "clocks": sampler.result(),
                 "seal_words": int(len(seal)), "peak_device_bytes": hal.bytes_peak()}
         print(json.dumps(line), flush=True)

@@ -71,7 +71,7 @@ struct PhaseScope {
   Ctx* c;
   cudaEvent_t b = nullptr;
   PhaseScope(Ctx* c_, const char* name, double bytes = 0) : c(c_) {
-    if (!c->profiling) return;
+    if (!c->profiling || !name) return;
     cudaEvent_t ev[2];
     for (int i = 0; i < 2; i++) {
       if (c->event_pool.empty()) {

@@ -10,6 +10,8 @@ import sys
 
 import numpy as np
 
+os.environ.setdefault("R0B200_PROFILE_PARTS", "1")
+
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from risc0_b200 import B200Hal  # noqa: E402
 

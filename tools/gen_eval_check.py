@@ -823,7 +823,7 @@ class Ptx:
         L.append(".address_size 64")
         L.append("")
         L.append(".visible .entry %s(" % self.name)
-        L.append("    .param .u64 p_check, .param .u64 p_accum, .param .u64 p_code, .param .u64 p_data, .param .u32 p_domain, .param .u32 p_first,")
+        L.append("    .param .u64 p_check, .param .u64 p_accum, .param .u64 p_code, .param .u64 p_data, .param .u32 p_domain, .param .u32 p_first, .param .u32 p_i0,")
         L.append("    .param .align 16 .b8 p_cst[%d])" % self.lay.size)
         L.append(".maxntid %d, 1, 1" % threads)
         if os.environ.get("EVAL_MAXNREG"):
@@ -835,7 +835,7 @@ class Ptx:
         L.append("    .reg .u32 %%l<%d>;" % (self.nl + 1))
         L.append("    .reg .u32 %%c<%d>;" % (self.ncopy + 2))
         L.append("    .reg .u64 %%w<%d>;" % (self.nw + 40))
-        L.append("    .reg .u32 %i, %domain, %mask, %first, %stride, %bdim, %bidx, %lane;")
+        L.append("    .reg .u32 %i, %i0, %domain, %mask, %first, %stride, %bdim, %bidx, %lane;")
         L.append("    .reg .u32 %o<8>, %q<8>, %iy<6>, %res<4>;")
         L.append("    .reg .u64 %check, %accum, %code, %data, %oaddr<4>, %off;")
         for (buf, back), base in sorted(self.bases.items()):
@@ -846,6 +846,7 @@ class Ptx:
         L.append("    ld.param.u64 %data, [p_data];")
         L.append("    ld.param.u32 %domain, [p_domain];")
         L.append("    ld.param.u32 %first, [p_first];")
+        L.append("    ld.param.u32 %i0, [p_i0];")
         L.append("    cvta.to.global.u64 %check, %check;")
         L.append("    cvta.to.global.u64 %accum, %accum;")
         L.append("    cvta.to.global.u64 %code, %code;")
@@ -854,6 +855,7 @@ class Ptx:
         L.append("    mov.u32 %bidx, %ctaid.x;")
         L.append("    mov.u32 %lane, %tid.x;")
         L.append("    mad.lo.u32 %i, %bidx, %bdim, %lane;")
+        L.append("    add.u32 %i, %i, %i0;")
         L.append("    setp.ge.u32 %p1, %i, %domain;")
         L.append("    @%p1 bra DONE;")
         L.append("    add.u32 %mask, %domain, -1;")
@@ -921,6 +923,7 @@ LAUNCHER = r"""// GENERATED by tools/gen_eval_check.py - do not edit. Circuit %(
 // The constraint polynomial is the sum of %(nparts)d groups of top-level terms; part j adds its group, already divided by
 // (3x)^N - 1, into `check` (part 0 stores). All per-proof constants travel in the kernel parameter block
 // (constant bank): poly_mix powers, their -11 multiples, globals, mix values and the 4 divisor inverses.
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -1007,14 +1010,24 @@ void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, cons
     cur = fp_mul(cur, R0_ROU_FWD_MONT[2]);
   }
   const unsigned threads = %(threads)d;
-  const unsigned blocks = (unsigned)((domain + threads - 1) / threads);
+  // Optional point tiles (EVAL_TILE_LG at generation time; default = whole domain): running all parts over a tile of
+  // 2^16 points keeps its tap columns (83 MB for rv32im) in L2 for the later parts and cuts DRAM traffic ~15x, but the
+  // 512-block launches it needs run at well under full occupancy: measured 26.1 ms per 2^20 points against 16.2 ms
+  // untiled (2^17: 21.0, 2^15: 35.3; gpurun_out/evalcheck_variants12.log), so it is off.
+  const size_t tile = std::min<size_t>(domain, size_t(1) << %(tile_lg)d);
   uint32_t domain32 = (uint32_t)domain;
-  for (int j = 0; j < kParts; j++) {
-    uint32_t first = j == 0 ? 1u : 0u;
-    void* args[] = {&check, &accum, &code, &data, &domain32, &first, &k};
-    PhaseScope part(c, kPartNames[j]);
-    R0_CUDA(cudaLaunchKernel((const void*)g_kernels[j], dim3(blocks), dim3(threads), args, 0, c->stream));
-    count_launch(c);
+  static const bool profile_parts = getenv("R0B200_PROFILE_PARTS") != nullptr;  // per-part timing is opt-in
+  for (size_t i0 = 0; i0 < domain; i0 += tile) {
+    const size_t npts = std::min(tile, domain - i0);
+    const unsigned blocks = (unsigned)((npts + threads - 1) / threads);
+    uint32_t base = (uint32_t)i0;
+    for (int j = 0; j < kParts; j++) {
+      uint32_t first = j == 0 ? 1u : 0u;
+      void* args[] = {&check, &accum, &code, &data, &domain32, &first, &base, &k};
+      PhaseScope part(c, profile_parts ? kPartNames[j] : nullptr);
+      R0_CUDA(cudaLaunchKernel((const void*)g_kernels[j], dim3(blocks), dim3(threads), args, 0, c->stream));
+      count_launch(c);
+    }
   }
 }
 """
@@ -1051,6 +1064,7 @@ def main():
         if f.startswith("eval_check_%s" % name):
             os.remove(os.path.join(gen_dir, f))
     externs, images, names = [], [], []
+    stats = dict(circuit=name, parts=len(parts), wide_multiplies=0, reductions=0, ptx_instructions=0, tap_loads=0)
     for j, part in enumerate(parts):
         S, outs = lower(dag, part["terms"], lay)
         if flatten:
@@ -1063,15 +1077,23 @@ def main():
         from collections import Counter
         cnt = Counter(S.nodes[i][0] for i in order)
         nprod = sum(len(S.nodes[i][1]) for i in order if S.nodes[i][0] == "d")
+        stats["wide_multiplies"] += nprod + cnt.get("*", 0) + 4      # dot terms, single products, output scaling
+        stats["reductions"] += cnt.get("d", 0) + cnt.get("*", 0) + 4
+        stats["ptx_instructions"] += sum(1 for ln in ptx.splitlines() if ln.startswith("    "))
+        stats["tap_loads"] += ptx.count("ld.global.nc.u32")
         print("part %d: %d terms, scalar ops %s, dot products %d" % (j, len(part["terms"]), dict(cnt), nprod))
         externs.append("extern const unsigned char r0_cubin_%s[];" % kname)
         images.append("r0_cubin_%s" % kname)
         names.append('"%s"' % kname)
     params = dict(name=name, NAME=name.upper(), nparts=len(parts), npm=npm, n_global=cfg["n_global"], n_mix=cfg["n_mix"],
-                  cst_size=lay.size, threads=threads, ncols=sum(cfg["cols"].values()), externs="\n".join(externs), images=", ".join(images),
+                  cst_size=lay.size, threads=threads, ncols=sum(cfg["cols"].values()),
+                  tile_lg=int(os.environ.get("EVAL_TILE_LG", "30")), externs="\n".join(externs), images=", ".join(images),
                   names=", ".join(names), part_names=", ".join('"eval_check_p%d"' % j for j in range(len(parts))))
     with open(os.path.join(gen_dir, "eval_check_%s.cu" % name), "w") as f:
         f.write(LAUNCHER % params)
+    # per-point operation counts of the emitted kernels (bench.py's INT32 roofline reads them)
+    with open(os.path.join(ROOT, "risc0_b200", "circuits", name + ".stats.json"), "w") as f:
+        json.dump(stats, f, indent=1)
 
 
 if __name__ == "__main__":
