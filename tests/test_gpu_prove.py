@@ -156,3 +156,14 @@ def test_prove_segment_max_sizes_properties(hal, po2):
     assert len(seal) == seal_words(po2)
     vroots = O.verify_rv32im(seal)
     assert np.array_equal(vroots, roots)
+
+
+def test_prove_segment_po2_18_bit_exact(hal):
+    # the largest size the CPU oracle (16 host cores) finishes in about a minute: every root, query position and seal
+    # word identical. po2 = 20 bit-exactness was checked once with tools/check_po2_20_bit_exact.py (profiles/).
+    po2 = 18
+    code, data, accum, glob = O.synthetic_witness(po2)
+    want_seal, want_roots, want_qpos = O.prove_rv32im(po2, code, data, accum, glob)
+    seal, roots, qpos = SegmentProver(hal).prove(po2, code, data, accum, glob)
+    assert np.array_equal(roots, want_roots) and np.array_equal(qpos, want_qpos)
+    assert np.array_equal(seal, want_seal)
