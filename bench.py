@@ -116,6 +116,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-po2", type=int, default=16, dest="cpu_po2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hash", default="poseidon2", choices=["poseidon2", "sha-256"],
+                    help="hash suite (the reference's default for rv32im segments is poseidon2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -135,7 +137,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    hal = B200Hal(local_rank, "poseidon2")
+    hal = B200Hal(local_rank, args.hash)
     prover = SegmentProver(hal)
     po2 = args.po2
     n = 1 << po2
@@ -275,7 +277,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": "rv32im segment po2=%d full prove_segment (NTT + Poseidon2 Merkle + eval_check + DEEP + FRI)" % po2,
                            "segments_per_step_per_gpu": 1, "user_cycles_per_segment": cycles, "total_cycles_per_segment": n,
-                           "hash": "poseidon2", "l2": "inputs (1.3 GB witness, 5.5 GB evaluations) exceed the 126 MB L2",
+                           "hash": args.hash, "l2": "inputs (1.3 GB witness, 5.5 GB evaluations) exceed the 126 MB L2",
                            "parallelism": "segments sharded one per GPU, no collective"},
                 "e2e": {"value": e2e_value, "unit": "cycles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(seal.nbytes),
                         "ms_per_step": e2e_ms / args.steps},
