@@ -62,6 +62,14 @@ __global__ void k(uint32_t* out, uint32_t a0, uint32_t b0) {
         uint32_t r = (uint32_t)(t >> 32) - h;
         uint32_t r2 = r + 0x78000001u;
         x[i] = r < r2 ? r : r2;
+      } else if (OP == 12) {  // Montgomery product, m = (lo + (lo << 27)) ^ (lo << 31): LEA + SHF + LOP3, no IMAD
+        uint64_t t = (uint64_t)x[i] * y[i];
+        uint32_t lo = (uint32_t)t;
+        uint32_t m = (lo + (lo << 27)) ^ (lo << 31);
+        uint32_t h = __umulhi(m, 0x78000001u);
+        uint32_t r = (uint32_t)(t >> 32) - h;
+        uint32_t r2 = r + 0x78000001u;
+        x[i] = r < r2 ? r : r2;
       } else if (OP == 10) {  // SHF / shl alone
         asm volatile("shl.b32 %0, %0, 3;" : "+r"(x[i]));
         asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
@@ -114,6 +122,7 @@ int main() {
   run<7>("IMAD.WIDE accumulate (cc pair)", 1, out, p.multiProcessorCount, ghz);
   run<8>("Montgomery product (5 instr)", 1, out, p.multiProcessorCount, ghz);
   run<9>("Montgomery product, m by shift-add", 1, out, p.multiProcessorCount, ghz);
+  run<12>("Montgomery product, m by LEA+SHF+LOP3", 1, out, p.multiProcessorCount, ghz);
   run<10>("shl + add", 2, out, p.multiProcessorCount, ghz);
   run<11>("xor + and (LOP3)", 2, out, p.multiProcessorCount, ghz);
   return 0;
