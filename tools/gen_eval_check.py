@@ -214,6 +214,57 @@ def partition(dag, uses, nparts, limit=None):
         best["terms"].append(u)
         best["cost"] = best_cost
         best["nodes"] |= r
+        best.setdefault("reaches", []).append(r)
+    # local refinement: move a unit to another bin when that lowers the total recomputed work (more sharing) and the
+    # receiving bin stays within 1.25x the unit limit
+    def bin_cost(reaches):
+        nodes = set()
+        for r in reaches:
+            nodes |= r
+        return sum(node_cost(dag, x) for x in nodes)
+
+    if os.environ.get("EVAL_REFINE", "1") == "1":
+        for _ in range(2):
+            moved = 0
+            for b in bins:
+                j = 0
+                while j < len(b["terms"]) and len(b["terms"]) > 1:
+                    r = b["reaches"][j]
+                    without = bin_cost(b["reaches"][:j] + b["reaches"][j + 1:])
+                    gain_here = b["cost"] - without
+                    best_t, best_delta, best_new = None, 0, None
+                    for t in bins:
+                        if t is b or not t["terms"]:
+                            continue
+                        new_cost = t["cost"] + sum(node_cost(dag, x) for x in r - t["nodes"])
+                        delta = (new_cost - t["cost"]) - gain_here
+                        if delta < best_delta and new_cost <= 1.25 * limit:
+                            best_t, best_delta, best_new = t, delta, new_cost
+                    if best_t is not None:
+                        best_t["terms"].append(b["terms"].pop(j))
+                        best_t["reaches"].append(b["reaches"].pop(j))
+                        best_t["nodes"] |= r
+                        best_t["cost"] = best_new
+                        b["cost"] = without
+                        b["nodes"] = set().union(*b["reaches"]) if b["reaches"] else set()
+                        moved += 1
+                    else:
+                        j += 1
+            if not moved:
+                break
+        # dissolve bins that ended up tiny (a launch plus the check read-modify-write costs more than they compute)
+        for b in sorted(bins, key=lambda b: b["cost"]):
+            if not b["terms"] or b["cost"] >= 0.3 * limit:
+                continue
+            for u, r in list(zip(b["terms"], b["reaches"])):
+                cands = [t for t in bins if t is not b and t["terms"]]
+                t = min(cands, key=lambda t: (t["cost"] + sum(node_cost(dag, x) for x in r - t["nodes"]) > 1.25 * limit,
+                                              sum(node_cost(dag, x) for x in r - t["nodes"])))
+                t["cost"] += sum(node_cost(dag, x) for x in r - t["nodes"])
+                t["terms"].append(u)
+                t["reaches"].append(r)
+                t["nodes"] |= r
+            b["terms"], b["reaches"], b["nodes"], b["cost"] = [], [], set(), 0
     return [b for b in bins if b["terms"]]
 
 
