@@ -224,7 +224,8 @@ def partition(dag, uses, nparts, limit=None):
         return sum(node_cost(dag, x) for x in nodes)
 
     if os.environ.get("EVAL_REFINE", "1") == "1":
-        for _ in range(2):
+        refine_cap = float(os.environ.get("EVAL_REFINE_CAP", "1.25"))
+        for _ in range(int(os.environ.get("EVAL_REFINE_PASSES", "2"))):
             moved = 0
             for b in bins:
                 j = 0
@@ -238,7 +239,7 @@ def partition(dag, uses, nparts, limit=None):
                             continue
                         new_cost = t["cost"] + sum(node_cost(dag, x) for x in r - t["nodes"])
                         delta = (new_cost - t["cost"]) - gain_here
-                        if delta < best_delta and new_cost <= 1.25 * limit:
+                        if delta < best_delta and new_cost <= refine_cap * limit:
                             best_t, best_delta, best_new = t, delta, new_cost
                     if best_t is not None:
                         best_t["terms"].append(b["terms"].pop(j))
@@ -256,6 +257,8 @@ def partition(dag, uses, nparts, limit=None):
         for b in sorted(bins, key=lambda b: b["cost"]):
             if not b["terms"] or b["cost"] >= 0.3 * limit:
                 continue
+            if not any(t is not b and t["terms"] for t in bins):
+                continue     # a single bin: nothing to merge into
             for u, r in list(zip(b["terms"], b["reaches"])):
                 cands = [t for t in bins if t is not b and t["terms"]]
                 t = min(cands, key=lambda t: (t["cost"] + sum(node_cost(dag, x) for x in r - t["nodes"]) > 1.25 * limit,
