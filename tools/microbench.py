@@ -52,20 +52,22 @@ def main():
                          frac_of_hbm_peak=round(gbs / peak, 3)))
         print("%-34s %-18s %9.3f ms %9.1f GB/s  (%.2f of %.0f)" % (op, shape, ms, gbs, gbs / peak, peak), flush=True)
 
-    ntt_shapes = [(16, 256), (18, 64), (20, 64), (22, 16)] if not a.quick else [(20, 32)]
+    ntt_shapes = [(16, 1), (16, 256), (18, 64), (20, 4), (20, 64), (20, 211), (22, 16), (24, 4)] if not a.quick else [(20, 32)]
     for lg, c in ntt_shapes:
         n = 1 << lg
         x = rand_dev(hal, n * c, 1)
         rec("batch_interpolate_ntt", "2^%d x %d" % (lg, c), timeit(hal, lambda: hal.batch_interpolate_ntt(x, c)), 8 * n * c)
         rec("batch_interpolate_ntt_zk", "2^%d x %d" % (lg, c), timeit(hal, lambda: hal.batch_interpolate_ntt_zk(x, c)), 8 * n * c)
         rec("batch_bit_reverse", "2^%d x %d" % (lg, c), timeit(hal, lambda: hal.batch_bit_reverse(x, c)), 8 * n * c)
-        y = hal.alloc_elem("y", 4 * n * c)
-        rec("batch_expand_into_evaluate_ntt", "2^%d x %d" % (lg, c),
-            timeit(hal, lambda: hal.batch_expand_into_evaluate_ntt(y, x, c, 2)), 20 * n * c)
+        y = None
+        if lg + 2 <= 24:  # 2^24 is the largest domain (MAX_CYCLES_PO2 = 22)
+            y = hal.alloc_elem("y", 4 * n * c)
+            rec("batch_expand_into_evaluate_ntt", "2^%d x %d" % (lg, c),
+                timeit(hal, lambda: hal.batch_expand_into_evaluate_ntt(y, x, c, 2)), 20 * n * c)
         cp = hal.alloc_elem("cp", n * c)
         rec("eltwise_copy_elem", "2^%d x %d" % (lg, c), timeit(hal, lambda: hal.eltwise_copy_elem(cp, x)), 8 * n * c)
         del x, y, cp
-    hash_shapes = [(22, 16), (22, 64), (22, 211), (18, 64)] if not a.quick else [(22, 16)]
+    hash_shapes = [(16, 64), (18, 64), (20, 103), (22, 1), (22, 16), (22, 64), (22, 211), (24, 16)] if not a.quick else [(22, 16)]
     for lg, c in hash_shapes:
         r = 1 << lg
         m = rand_dev(hal, r * c, 2)
