@@ -182,12 +182,22 @@ def main():
 
     keep = [pinned(code), pinned(data), pinned(accum)]
     h_code, h_data, h_accum = (k[1] for k in keep)
-    for _ in range(min(args.warmup, 2)):
-        prover.prove(po2, h_code, h_data, h_accum, glob)
+    # depth-2 pipeline, as the reference's worker queues do: the upload of step s+1 is enqueued (copy stream) before
+    # step s is proved, so all but the first transfer overlap compute. Every step's H2D copy and seal D2H are inside
+    # the timed region.
+    def e2e_steps(k):
+        up = prover.upload(po2, h_code, h_data, h_accum)
+        out = None
+        for s_ in range(k):
+            nxt = prover.upload(po2, h_code, h_data, h_accum) if s_ + 1 < k else None
+            out = prover.prove_uploaded(up, glob)[0]
+            up = nxt
+        return out
+
+    e2e_steps(min(args.warmup, 2))
     barrier()
     hal.timer_start()
-    for _ in range(args.steps):
-        seal, _, _ = prover.prove(po2, h_code, h_data, h_accum, glob)
+    seal = e2e_steps(args.steps)
     e2e_ms = hal.timer_stop()
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
@@ -280,7 +290,10 @@ def main():
                            "hash": args.hash, "l2": "inputs (1.3 GB witness, 5.5 GB evaluations) exceed the 126 MB L2",
                            "parallelism": "segments sharded one per GPU, no collective"},
                 "e2e": {"value": e2e_value, "unit": "cycles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(seal.nbytes),
-                        "ms_per_step": e2e_ms / args.steps},
+                        "ms_per_step": e2e_ms / args.steps,
+                        "pipeline": "depth 2: the H2D copy of step s+1 is enqueued on a copy stream before step s is proved "
+                                    "(r0b200_witness_upload / r0b200_prove_uploaded); all K uploads and K seal reads are "
+                                    "inside the timed region"},
                 "gpu_launches": int(launches), "roofline": roofline, "int32_roofline": int32, "cpu_baseline": cpu_baseline,
                 "phase_ms_per_step": phase_ms, "phase_alg_GBps": phase_gbs, "clocks": sampler.result(),
                 "seal_words": int(len(seal)), "peak_device_bytes": hal.bytes_peak()}

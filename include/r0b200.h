@@ -158,6 +158,20 @@ r0b200_err r0b200_prove_recursion(r0b200_ctx* ctx, int hash, uint32_t po2, const
                                   uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
                                   size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host);
 
+/* ---- pipelined host witnesses ----
+ * The reference keeps the GPU busy with depth-2 work queues (r0vm/src/actors/worker.rs:70-76,185-204): while segment s is
+ * proved, segment s+1 is prepared. r0b200_witness_upload() enqueues the host->device copy of a witness (circuit 0 =
+ * rv32im, 1 = recursion; column-major host matrices, pinned memory makes the copies asynchronous) on the context's
+ * copy stream and returns at once; r0b200_prove_uploaded() consumes it (the handle's buffers pass to the proof; free
+ * the handle afterwards). Uploading s+1 before proving s hides the PCIe transfer behind compute. */
+typedef struct r0b200_witness r0b200_witness;
+r0b200_err r0b200_witness_upload(r0b200_ctx* ctx, int circuit, uint32_t po2, const uint32_t* code_host,
+                                 const uint32_t* data_host, const uint32_t* accum_host, r0b200_witness** out);
+void r0b200_witness_free(r0b200_witness* witness);
+r0b200_err r0b200_prove_uploaded(r0b200_ctx* ctx, int hash, r0b200_witness* witness, const uint32_t* global_host,
+                                 uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
+                                 size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,7 @@ def load_library():
             fn.restype = C.c_void_p
         _lib.r0b200_destroy.restype = None
         _lib.r0b200_free_error.restype = None
+        _lib.r0b200_witness_free.restype = None
         _lib.r0b200_launch_count.restype = C.c_uint64
         _lib.r0b200_bytes_peak.restype = C.c_uint64
         _lib.r0b200_stream.restype = C.c_void_p

@@ -35,8 +35,10 @@ struct DevBuf {
   uint32_t* p = nullptr;
   size_t words = 0;
   DevBuf() {}
-  DevBuf(Ctx* c_, size_t words_) : c(c_), words(words_) {
-    R0_CUDA(cudaMallocAsync(&p, (words ? words : 4) * 4, c->stream));
+  // `alloc_stream`: the stream the allocation is ordered on (default: the compute stream). The buffer is always
+  // released on the compute stream, after the kernels that used it.
+  DevBuf(Ctx* c_, size_t words_, cudaStream_t alloc_stream = nullptr) : c(c_), words(words_) {
+    R0_CUDA(cudaMallocAsync(&p, (words ? words : 4) * 4, alloc_stream ? alloc_stream : c->stream));
     c->bytes_allocated += words * 4;
     if (c->bytes_allocated > c->bytes_peak) c->bytes_peak = c->bytes_allocated;
   }
@@ -224,6 +226,24 @@ struct PolyGroup {
   size_t count = 0;
 };
 
+}  // namespace
+}  // namespace r0
+
+// A witness whose host->device upload has been enqueued on the context's copy stream (r0b200_witness_upload): the
+// three coefficient buffers a proof starts from, plus one event per uploaded column chunk. Allocation and copies are
+// ordered on the copy stream only, so they overlap whatever the compute stream is doing (the previous proof).
+struct r0b200_witness {
+  r0::Ctx* c = nullptr;
+  uint32_t po2 = 0;
+  int circuit = 0;  // 0 = rv32im, 1 = recursion
+  uint32_t* coeffs[3] = {nullptr, nullptr, nullptr};
+  size_t words[3] = {0, 0, 0};
+  std::vector<cudaEvent_t> events[3];
+};
+
+namespace r0 {
+namespace {
+
 class SegmentProver {
  public:
   SegmentProver(Ctx* c, const CircuitDesc& desc, int hash, size_t po2)
@@ -257,6 +277,20 @@ class SegmentProver {
       R0_CUDA(cudaEventRecord(ev, c_->copy_stream));
       uploads_[g].push_back(ev);
     }
+  }
+  // take over group g's buffer and chunk events from an uploaded witness (r0b200_witness_upload)
+  void adopt_group(size_t g, r0b200_witness* w) {
+    PolyGroup& pg = groups_[g];
+    pg.count = taps_.group_sizes[g];
+    R0_CHECK(w->words[g] == pg.count * cycles_, "uploaded witness does not match the circuit / po2");
+    pg.coeffs.c = c_;
+    pg.coeffs.p = w->coeffs[g];
+    pg.coeffs.words = w->words[g];
+    c_->bytes_allocated += w->words[g] * 4;
+    if (c_->bytes_allocated > c_->bytes_peak) c_->bytes_peak = c_->bytes_allocated;
+    w->coeffs[g] = nullptr;
+    uploads_[g] = std::move(w->events[g]);
+    w->events[g].clear();
   }
   size_t upload_chunk_cols() const {
     size_t cols = (size_t(64) << 20) / (cycles_ * 4);   // about 64 MB per chunk
@@ -474,7 +508,8 @@ class SegmentProver {
 using namespace r0;
 
 static void prove_segment(r0b200_ctx* ctx, const CircuitDesc& desc, int hash, uint32_t po2, const uint32_t* code,
-                          const uint32_t* data, const uint32_t* accum, int witness_on_host, const uint32_t* global_host,
+                          const uint32_t* data, const uint32_t* accum, int witness_on_host, r0b200_witness* uploaded,
+                          const uint32_t* global_host,
                           uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
                           size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host) {
   R0_CHECK(ctx != nullptr, "null r0b200 context");
@@ -499,8 +534,13 @@ static void prove_segment(r0b200_ctx* ctx, const CircuitDesc& desc, int hash, ui
   header[desc.output_size] = po2;
   iop.commit(suite.hash_words(header.data(), header.size()));
   iop.write(header.data(), header.size());
-  const bool on_host = witness_on_host != 0;
-  if (on_host) {
+  const bool on_host = witness_on_host != 0 || uploaded != nullptr;
+  if (uploaded) {
+    R0_CHECK(uploaded->c == ctx && uploaded->po2 == po2, "uploaded witness belongs to another context or size");
+    prover.adopt_group(1, uploaded);
+    prover.adopt_group(2, uploaded);
+    prover.adopt_group(0, uploaded);
+  } else if (on_host) {
     // uploads are enqueued up front in consumption order; each group's compute waits only for its own chunks
     prover.prefetch_group(1, code);
     prover.prefetch_group(2, data);
@@ -530,8 +570,8 @@ extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po
                                           size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
                                           uint32_t* query_pos_out_host) {
   R0_API_BEGIN
-  prove_segment(ctx, kRv32im, hash, po2, code, data, accum, witness_on_host, global_host, seal_out_host, seal_cap, seal_len,
-                roots_out_host, roots_cap, nroots, query_pos_out_host);
+  prove_segment(ctx, kRv32im, hash, po2, code, data, accum, witness_on_host, nullptr, global_host, seal_out_host, seal_cap,
+                seal_len, roots_out_host, roots_cap, nroots, query_pos_out_host);
   R0_API_END
 }
 
@@ -541,7 +581,65 @@ extern "C" r0b200_err r0b200_prove_recursion(r0b200_ctx* ctx, int hash, uint32_t
                                              size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap,
                                              size_t* nroots, uint32_t* query_pos_out_host) {
   R0_API_BEGIN
-  prove_segment(ctx, kRecursion, hash, po2, ctrl, data, accum, witness_on_host, global_host, seal_out_host, seal_cap,
-                seal_len, roots_out_host, roots_cap, nroots, query_pos_out_host);
+  prove_segment(ctx, kRecursion, hash, po2, ctrl, data, accum, witness_on_host, nullptr, global_host, seal_out_host,
+                seal_cap, seal_len, roots_out_host, roots_cap, nroots, query_pos_out_host);
+  R0_API_END
+}
+
+// ---- pipelined host witnesses: upload segment s+1 while segment s is being proved ---------------------------------
+extern "C" r0b200_err r0b200_witness_upload(r0b200_ctx* ctx, int circuit, uint32_t po2, const uint32_t* code_host,
+                                            const uint32_t* data_host, const uint32_t* accum_host, r0b200_witness** out) {
+  R0_API_BEGIN
+  R0_CHECK(ctx != nullptr && out != nullptr, "witness_upload: null argument");
+  R0_CHECK(circuit == 0 || circuit == 1, "witness_upload: unknown circuit");
+  R0_CHECK(po2 >= 9 && po2 + 2 <= (uint32_t)MAX_LG, "witness_upload: po2 out of range");
+  R0_CUDA(cudaSetDevice(ctx->device));
+  const CircuitDesc& desc = circuit == 0 ? kRv32im : kRecursion;
+  const size_t cycles = size_t(1) << po2;
+  std::unique_ptr<r0b200_witness> w(new r0b200_witness());
+  w->c = ctx;
+  w->po2 = po2;
+  w->circuit = circuit;
+  const uint32_t* src[3] = {accum_host, code_host, data_host};   // tap-group order: accum, code, data
+  size_t chunk = (size_t(64) << 20) / (cycles * 4);
+  if (chunk == 0) chunk = 1;
+  const int order[3] = {1, 2, 0};                                // consumption order: code, data, accum
+  for (int oi = 0; oi < 3; oi++) {
+    const int g = order[oi];
+    const size_t count = desc.group_sizes[g];
+    w->words[g] = count * cycles;
+    R0_CUDA(cudaMallocAsync(&w->coeffs[g], w->words[g] * 4, ctx->copy_stream));
+    for (size_t c0 = 0; c0 < count; c0 += chunk) {
+      const size_t nc = std::min(chunk, count - c0);
+      R0_CUDA(cudaMemcpyAsync(w->coeffs[g] + c0 * cycles, src[g] + c0 * cycles, nc * cycles * 4, cudaMemcpyHostToDevice,
+                              ctx->copy_stream));
+      cudaEvent_t ev;
+      R0_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      R0_CUDA(cudaEventRecord(ev, ctx->copy_stream));
+      w->events[g].push_back(ev);
+    }
+  }
+  *out = w.release();
+  R0_API_END
+}
+
+extern "C" void r0b200_witness_free(r0b200_witness* w) {
+  if (!w) return;
+  cudaSetDevice(w->c->device);
+  for (int g = 0; g < 3; g++) {
+    for (cudaEvent_t ev : w->events[g]) cudaEventDestroy(ev);
+    if (w->coeffs[g]) cudaFreeAsync(w->coeffs[g], w->c->copy_stream);
+  }
+  delete w;
+}
+
+extern "C" r0b200_err r0b200_prove_uploaded(r0b200_ctx* ctx, int hash, r0b200_witness* witness, const uint32_t* global_host,
+                                            uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len,
+                                            uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
+                                            uint32_t* query_pos_out_host) {
+  R0_API_BEGIN
+  R0_CHECK(witness != nullptr, "prove_uploaded: null witness");
+  prove_segment(ctx, witness->circuit == 0 ? kRv32im : kRecursion, hash, witness->po2, nullptr, nullptr, nullptr, 1, witness,
+                global_host, seal_out_host, seal_cap, seal_len, roots_out_host, roots_cap, nroots, query_pos_out_host);
   R0_API_END
 }

@@ -341,6 +341,34 @@ class SegmentProver:
     # (code/ctrl, data, accum) column counts and global words per circuit
     SHAPES = {"rv32im": (1, 211, 103, 90), "recursion": (23, 128, 12, 32)}
 
+    def upload(self, po2, code, data, accum, circuit="rv32im"):
+        """enqueue the host->device copy of a witness (numpy arrays, ideally views of pinned memory that stay alive until
+        the proof has run) and return a handle for prove(uploaded=...). Call it for segment s+1 before proving segment s
+        to hide the transfer behind compute (the reference's depth-2 queues, r0vm/src/actors/worker.rs:70-76)."""
+        hal = self.hal
+        n = 1 << po2
+        c_code, c_data, c_accum, _ = self.SHAPES[circuit]
+        code, data, accum = _u32(code), _u32(data), _u32(accum)
+        assert code.size == c_code * n and data.size == c_data * n and accum.size == c_accum * n
+        h = C.c_void_p()
+        check(hal._l.r0b200_witness_upload(hal._ctx, C.c_int(0 if circuit == "rv32im" else 1), C.c_uint32(po2),
+                                           _np_ptr(code), _np_ptr(data), _np_ptr(accum), C.byref(h)))
+        return (h, (code, data, accum))   # keep the host arrays alive with the handle
+
+    def prove_uploaded(self, uploaded, glob):
+        hal = self.hal
+        h, _keep = uploaded
+        glob = _u32(glob)
+        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
+        try:
+            check(hal._l.r0b200_prove_uploaded(hal._ctx, hal.hash, h, _np_ptr(glob), _np_ptr(self._seal),
+                                               C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots),
+                                               C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
+        finally:
+            hal._l.r0b200_witness_free(h)
+        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
+                self._qpos.copy())
+
     def prove(self, po2, code, data, accum, glob, circuit="rv32im"):
         """returns (seal words, committed roots [k, 8], drawn query positions [50]). circuit = "rv32im"
         (prove_core, rv32im/src/prove/hal/mod.rs:171-222) or "recursion" (recursion/src/prove/mod.rs:179-224)"""

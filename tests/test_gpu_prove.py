@@ -167,3 +167,20 @@ def test_prove_segment_po2_18_bit_exact(hal):
     seal, roots, qpos = SegmentProver(hal).prove(po2, code, data, accum, glob)
     assert np.array_equal(roots, want_roots) and np.array_equal(qpos, want_qpos)
     assert np.array_equal(seal, want_seal)
+
+
+def test_pipelined_upload_matches_direct_prove(hal):
+    # r0b200_witness_upload + r0b200_prove_uploaded: two segments in flight (upload of the second overlaps the proof
+    # of the first); seals identical with the direct host-witness path
+    po2 = 12
+    w1 = O.synthetic_witness(po2)
+    w2 = O.synthetic_witness(po2, seed=1234)
+    prover = SegmentProver(hal)
+    want1 = prover.prove(po2, *w1)[0]
+    want2 = prover.prove(po2, *w2)[0]
+    u1 = prover.upload(po2, w1[0], w1[1], w1[2])
+    u2 = prover.upload(po2, w2[0], w2[1], w2[2])
+    got1 = prover.prove_uploaded(u1, w1[3])[0]
+    got2 = prover.prove_uploaded(u2, w2[3])[0]
+    assert np.array_equal(got1, want1) and np.array_equal(got2, want2)
+    assert not np.array_equal(got1, got2)
