@@ -37,6 +37,7 @@ struct Tables {
   // two-level twiddle tables for the order-2^24 roots: w^E = hi[E >> 12] * lo[E & 4095]; dir 0 = ROU_REV, 1 = ROU_FWD
   uint32_t* tw_lo[2];
   uint32_t* tw_hi[2];
+  uint32_t* tw_row[2];  // inter-step twiddle rows (ntt.cu: row_off)
   // powers of three, same two-level split: 3^e = p3_hi[e >> 12] * p3_lo[e & 4095]
   uint32_t* p3_lo;
   uint32_t* p3_hi;
