@@ -24,7 +24,10 @@
 #define R0_NTT_THREADS 256
 #endif
 #ifndef R0_NTT_STRIDED_THREADS
-#define R0_NTT_STRIDED_THREADS R0_NTT_THREADS
+#define R0_NTT_STRIDED_THREADS R0_NTT_THREADS   // strided-pass block size for k1 <= 10
+#endif
+#ifndef R0_NTT_BIG_STRIDED
+#define R0_NTT_BIG_STRIDED 1   // k1 = 11, 12: 8-column tiles (32 B segments) in blocks of 512 / 1024 threads
 #endif
 #ifndef R0_NTT_ROWTW
 #define R0_NTT_ROWTW 1   // inter-step twiddles from per-step row tables (vector loads) instead of 15 scalar gathers
@@ -542,7 +545,11 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_inv_contig_kernel(NttArgs a) 
 //  DIR 1: standalone DIT down the rows (inputs were pre-twiddled by the contiguous pass).
 template <int M>
 struct StridedCfg {
-  static constexpr int LGT = M <= 10 ? R0_NTT_LGT_SMALL : (M == 11 ? 3 : 2);
+  // 2^LGT adjacent columns per tile. A tile of 2^12 rows x 8 columns is 139 KB: one block per SM, so the block is made
+  // large enough (1024 threads, 2 items per thread and step) to keep the SM busy on its own.
+  static constexpr int LGT = M <= 10 ? R0_NTT_LGT_SMALL : (R0_NTT_BIG_STRIDED ? 3 : (M == 11 ? 3 : 2));
+  static constexpr int THREADS =
+      M <= 10 || !R0_NTT_BIG_STRIDED ? R0_NTT_STRIDED_THREADS : (M == 11 ? 512 : 1024);
   static constexpr int LAST_A = M >= 4 ? 4 : M;   // radix of the inverse transform's last step (stride 1)
   static constexpr bool STEP_TW = M > 4;          // a barrier separates strided_prep from the last step
   static constexpr size_t SMEM = (((size_t)pad_size(M) << LGT) + (STEP_TW ? (size_t(1) << (LGT + LAST_A)) : 0)) * 4;
@@ -554,7 +561,7 @@ __device__ __forceinline__ void strided_prep(const NttArgs& a, uint32_t* s, uint
   using C = StridedCfg<M>;
   if constexpr (C::STEP_TW) {
     uint32_t* sx = s + (pad_size(M) << C::LGT);
-    for (int w = threadIdx.x; w < (1 << (C::LGT + C::LAST_A)); w += R0_NTT_STRIDED_THREADS) {
+    for (int w = threadIdx.x; w < (1 << (C::LGT + C::LAST_A)); w += C::THREADS) {
       const uint32_t L = L0 + (w >> C::LAST_A);
       const uint32_t j = w & ((1 << C::LAST_A) - 1);
       const uint32_t bj = __brev(j) >> (32 - C::LAST_A);
@@ -571,7 +578,7 @@ __device__ __forceinline__ void strided_step(const NttArgs& a, uint32_t* s, uint
   constexpr int ITEMS = G::ITEMS_PER_TILE;
   constexpr int PS = pstride(S) * T;
 #pragma unroll 1
-  for (int w = threadIdx.x; w < ITEMS; w += R0_NTT_STRIDED_THREADS) {
+  for (int w = threadIdx.x; w < ITEMS; w += StridedCfg<M>::THREADS) {
     int t, l, r, base;
     G::decode(w, t, l, r, base);
     uint32_t v[1 << A];
@@ -618,7 +625,7 @@ __device__ __forceinline__ void strided_step(const NttArgs& a, uint32_t* s, uint
 }
 
 template <int M, int DIR>
-__global__ void __launch_bounds__(R0_NTT_STRIDED_THREADS) ntt_strided_kernel(NttArgs a) {
+__global__ void __launch_bounds__(StridedCfg<M>::THREADS) ntt_strided_kernel(NttArgs a) {
   extern __shared__ uint32_t s[];
   constexpr int Q = M / 4, REM = M % 4;
   constexpr int LGT = StridedCfg<M>::LGT;
@@ -878,7 +885,7 @@ template <int M, int DIR>
 static void launch_strided(Ctx* c, const NttArgs& a, size_t ncols) {
   set_smem(ntt_strided_kernel<M, DIR>, StridedCfg<M>::SMEM);
   dim3 grid(1u << (a.k2 - StridedCfg<M>::LGT), (unsigned)ncols);
-  ntt_strided_kernel<M, DIR><<<grid, R0_NTT_STRIDED_THREADS, StridedCfg<M>::SMEM, c->stream>>>(a);
+  ntt_strided_kernel<M, DIR><<<grid, StridedCfg<M>::THREADS, StridedCfg<M>::SMEM, c->stream>>>(a);
 }
 
 static void dispatch_inv_contig(Ctx* c, const NttArgs& a) {

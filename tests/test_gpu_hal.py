@@ -116,11 +116,12 @@ def test_batch_evaluate_any_small(hal, lg, polys, evals):
     assert np.array_equal(out.view(), O.batch_evaluate_any(coeffs, polys, which, xs))
 
 
-def test_mix_poly_coeffs(hal):
+@pytest.mark.parametrize("count", [1 << 12, 1002, 7, 4])   # multiples of 4 take the 128-bit kernel, the others the scalar one
+def test_mix_poly_coeffs(hal, count):
     # hal testutil: 16 x 2^14 inputs -> (100 + 1) combos x 2^12 ... we keep its structure: several inputs per combo,
     # non-zero initial output, unsorted combo ids
-    rng = rng_for("mix")
-    input_size, count, combo_count = 37, 1 << 12, 6
+    rng = rng_for("mix", count)
+    input_size, combo_count = 37, 6
     inp = O.rand_elems(rng, input_size * count)
     combos = rng.integers(0, combo_count, size=input_size).astype(np.uint32)
     out0 = O.rand_elems(rng, 4 * combo_count * count)
