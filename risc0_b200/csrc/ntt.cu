@@ -5,18 +5,21 @@
 //           core/ntt.rs:284-343), Hal::batch_bit_reverse (cpu.rs:352-360); reference GPU path: per-column host loops
 //           over sppark NTTs (risc0/sys/kernels/zkp/cuda/supra/ntt.cu:34-152).
 //
-// Design (modelled and checked against the oracle in tools/ntt_model.py):
-//  * four-step split n = 2^k1 * 2^k2: one "strided" pass over tiles of 2^k1 rows x T adjacent columns and one
-//    "contiguous" pass over 2^k2-element tiles; n <= 2^12 needs only the contiguous pass. All columns of a batch are
-//    processed by one launch (grid.y = columns), not a host loop.
-//  * inside a tile the 2^m-point transform runs in shared memory as radix-16 register steps (4 butterfly layers per
-//    shared-memory round trip, constant twiddles from the constant bank, inter-step twiddles from a 16 KB table),
-//    padded (i + i/16) so every step is bank-conflict free or 2-way at worst.
-//  * everything that would be an extra HBM pass in the reference is fused into an epilogue: the 1/n scale and the
-//    zk shift 3^brev(i) into the iNTT's last store, the expand-by-4 into the LDE's first load (the two skipped
-//    butterfly layers become a template parameter), the inter-pass twiddle into the producing pass.
-//  * algorithmic HBM bytes: iNTT 8 B/element, LDE 20 B/input element; two-pass sizes move 16 / 52 B unless the
-//    caller launches column groups that fit the 126 MB L2 (`cols_per_launch`), which keeps the intermediate on chip.
+// Design (modelled and checked against the oracle in tools/ntt_model.py; tuning history in profiles/r1_ntt_sweep*.log):
+//  * four-step split n = 2^k1 * 2^k2: one "contiguous" pass over 2^k2-element tiles (k2 = 12 whenever n allows: three
+//    radix-16 steps) and one "strided" pass over tiles of 2^k1 rows x 8 adjacent columns; n <= 2^12 needs only the
+//    contiguous pass. All columns of a batch are processed by one launch per pass (grid.y = columns), not a host loop.
+//  * inside a tile the 2^m-point transform runs as radix-16 register steps (4 butterfly layers per shared-memory round
+//    trip, sixteenth roots from the constant bank, inter-step twiddles as one contiguous table row per thread fetched
+//    with 128-bit loads); shared memory is padded (i + i/16) so every step is bank-conflict free or 2-way at worst.
+//  * sums / differences that only feed a twiddle product stay unreduced (lazy_add / lazy_sub).
+//  * everything that would be an extra HBM pass in the reference is fused: the 1/n scale and the zk shift 3^brev(i)
+//    into the iNTT's last store, the expand-by-4 into the LDE's first load (the two skipped butterfly layers become a
+//    template parameter), the inter-pass twiddle into the producing pass (one lookup per thread x 16 per-tile factors
+//    staged in shared memory).
+//  * algorithmic HBM bytes: iNTT 8 B/element, LDE 20 B/input element; two-pass sizes move 16 / 52 B. The kernels are
+//    bound by the integer pipes (ncu: fmaheavy 69-79 %, DRAM <= 37 %), so the intermediate is NOT kept in L2 by
+//    splitting the batch into column groups any more - that only cost tail waves (R0_NTT_L2_MB re-enables it).
 #include "ctx.h"
 
 // Compile-time tuning knobs (tools/sweep_ntt.sh builds variants; the defaults are the measured best).

@@ -27,6 +27,7 @@ How it is computed differs from both reference back ends:
 import gzip
 import json
 import os
+import re
 import sys
 
 sys.setrecursionlimit(200000)
@@ -894,6 +895,8 @@ class Ptx:
         L.append("    .reg .u64 %check, %accum, %code, %data, %oaddr<4>, %off;")
         for (buf, back), base in sorted(self.bases.items()):
             L.append("    .reg .u64 %s;" % base)
+        if int(os.environ.get("EVAL_PREFETCH", "0")):
+            L.append("    .reg .u64 %pfa;")
         L.append("    ld.param.u64 %check, [p_check];")
         L.append("    ld.param.u64 %accum, [p_accum];")
         L.append("    ld.param.u64 %code, [p_code];")
@@ -922,7 +925,7 @@ class Ptx:
             L.append("    and.b32 %q0, %q0, %mask;")
             L.append("    mad.wide.u32 %s, %%q0, 4, %%%s;" % (base, buf))
             n += 1
-        L.extend(self.body)
+        L.extend(self.with_prefetch(self.body))
         # scale by inv_y[i & 3], accumulate into check unless this is the first part
         L.append("    and.b32 %q1, %i, 3;")
         L.append("    ld.param.u32 %%iy0, [p_cst+%d];" % self.lay.inv_y)
@@ -962,6 +965,58 @@ class Ptx:
         L.append("    ret;")
         L.append("}")
         return "\n".join(L) + "\n"
+
+    def with_prefetch(self, body):
+        """EVAL_PREFETCH=1|2: for every fence-delimited window, prefetch (L1 | L2) the tap lines the NEXT window loads,
+        spread over the first half of the current window. The loads themselves stay where they are (right before
+        first use, no extra live registers); the prefetch only turns their DRAM / L2 latency into an L1 / L2 hit."""
+        level = int(os.environ.get("EVAL_PREFETCH", "0"))
+        if not level:
+            return body
+        fence_lines = ("@%p0 bra DONE;", "bar.sync 0;")
+        windows = [[]]
+        for ln in body:
+            windows[-1].append(ln)
+            if ln.strip() in fence_lines:
+                windows.append([])
+        pat = re.compile(r"\s*mad\.wide\.u32 (%w\d+), %stride, (\d+), (%b_\w+);")
+
+        def taps(w):
+            seen, order = set(), []
+            for j, ln in enumerate(w):
+                if "ld.global.nc.u32" in ln:
+                    m = pat.match(w[j - 1])
+                    key = (m.group(2), m.group(3))
+                    if key not in seen:
+                        seen.add(key)
+                        order.append(key)
+            return order
+
+        out = []
+        self.uses_prefetch = True
+        for wi, w in enumerate(windows):
+            pf = []
+            if wi + 1 < len(windows):
+                here = set(taps(w)) if level < 3 else set()
+                pf = [k for k in taps(windows[wi + 1]) if k not in here]
+            if not pf:
+                out.extend(w)
+                continue
+            step = max(1, (len(w) // 2) // len(pf))
+            k = 0
+            for j, ln in enumerate(w):
+                # never between a mad.wide and the load that uses it, or inside a carry chain (.cc / madc pairs)
+                prev = w[j - 1] if j else ""
+                if k < len(pf) and j >= k * step and ".cc." not in prev and "madc" not in ln and "ld.global.nc" not in ln:
+                    col, base = pf[k]
+                    out.append("    mad.wide.u32 %%pfa, %%stride, %s, %s;" % (col, base))
+                    out.append("    prefetch.global.%s [%%pfa];" % ("L2" if level == 2 else "L1"))
+                    k += 1
+                out.append(ln)
+            for col, base in pf[k:]:
+                out.append("    mad.wide.u32 %%pfa, %%stride, %s, %s;" % (col, base))
+                out.append("    prefetch.global.%s [%%pfa];" % ("L2" if level == 2 else "L1"))
+        return out
 
     def _mat(self, i):
         m = self.t()
