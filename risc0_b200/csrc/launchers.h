@@ -37,6 +37,8 @@ void r0_combos_prepare(r0::Ctx* c, uint32_t* combos, const r0::FpExt* coeff_u_ho
                        uint32_t combo_count, size_t cycles, const uint32_t* reg_sizes, const uint32_t* reg_combo_ids,
                        uint32_t nregs, const r0::FpExt& mix, uint32_t check_size);
 void r0_poly_divide(r0::Ctx* c, uint32_t* poly, size_t n, const r0::FpExt& z, uint32_t* remainder_dev);
+void r0_poly_divide_batch(r0::Ctx* c, uint32_t* const* polys, const r0::FpExt* zs, uint32_t* const* remainders_dev,
+                          size_t njobs, size_t n);
 // job j: dst[dst_off + g] = src[g * stride + idx] for g < size   (one MerkleTreeProver::prove column read)
 struct GatherJob {
   const uint32_t* src;

@@ -301,9 +301,19 @@ __device__ __forceinline__ FpExt div_local(const FpExt* p, size_t n, size_t lo, 
   return acc;
 }
 
-__global__ void __launch_bounds__(DIV_B) k_div_block_totals(FpExt* totals, const FpExt* p, size_t n, const DivPowers* pw) {
+// Independent divisions (different combos) run side by side: blockIdx.y (blockIdx.x for the one-block carry kernel)
+// selects the job; every job has the same length n.
+struct DivJob {
+  FpExt* p;
+  FpExt* remainder;
+};
+
+__global__ void __launch_bounds__(DIV_B) k_div_block_totals(FpExt* totals, const DivJob* jobs, size_t n, const DivPowers* pw) {
   __shared__ FpExt sh[DIV_B];
   const int t = threadIdx.x;
+  const FpExt* p = jobs[blockIdx.y].p;
+  pw += blockIdx.y;
+  totals += (size_t)blockIdx.y * gridDim.x;
   const size_t lo = ((size_t)blockIdx.x * DIV_B + t) * DIV_E;
   FpExt c[DIV_E];
   sh[t] = div_local(p, n, lo, pw->z, c);
@@ -323,6 +333,9 @@ __global__ void __launch_bounds__(1024) k_div_block_carries(FpExt* carry, const 
   __shared__ FpExt sh[2][1024];
   __shared__ FpExt above;  // carry entering the current window from the blocks above it
   const int t = threadIdx.x;
+  pw += blockIdx.x;
+  totals += (size_t)blockIdx.x * nblocks;
+  carry += (size_t)blockIdx.x * nblocks;
   if (t == 0) above = ext_zero();
   const size_t nwin = (nblocks + 1023) / 1024;
   for (size_t wi = nwin; wi-- > 0;) {
@@ -353,10 +366,14 @@ __global__ void __launch_bounds__(1024) k_div_block_carries(FpExt* carry, const 
   }
 }
 
-__global__ void __launch_bounds__(DIV_B) k_div_quotient(FpExt* p, size_t n, const FpExt* carry, const DivPowers* pw,
-                                                        FpExt* remainder) {
+__global__ void __launch_bounds__(DIV_B) k_div_quotient(const DivJob* jobs, size_t n, const FpExt* carry,
+                                                        const DivPowers* pw) {
   __shared__ FpExt sh[2][DIV_B];
   const int t = threadIdx.x;
+  FpExt* p = jobs[blockIdx.y].p;
+  FpExt* remainder = jobs[blockIdx.y].remainder;
+  pw += blockIdx.y;
+  carry += (size_t)blockIdx.y * gridDim.x;
   const size_t lo = ((size_t)blockIdx.x * DIV_B + t) * DIV_E;
   const FpExt z = pw->z;
   FpExt c[DIV_E];
@@ -581,39 +598,53 @@ void r0_combos_prepare(Ctx* c, uint32_t* combos, const FpExt* coeff_u_host, size
   R0_CUDA(cudaGetLastError());
 }
 
-// poly: n FpExt coefficients, divided in place by (x - z); the remainder is written to *remainder_dev.
-void r0_poly_divide(Ctx* c, uint32_t* poly, size_t n, const FpExt& z, uint32_t* remainder_dev) {
-  if (n == 0) return;
-  PhaseScope ph(c, "combos_divide", 32.0 * (double)n);
+// polys[j]: n FpExt coefficients, divided in place by (x - zs[j]); the remainders go to remainders_dev[j]. The jobs must
+// be independent (different polynomials); successive divisions of one polynomial are successive calls.
+void r0_poly_divide_batch(Ctx* c, uint32_t* const* polys, const FpExt* zs, uint32_t* const* remainders_dev, size_t njobs,
+                          size_t n) {
+  if (n == 0 || njobs == 0) return;
+  PhaseScope ph(c, "combos_divide", 32.0 * (double)n * (double)njobs);
   const size_t nblocks = (n + DIV_SEG - 1) / DIV_SEG;
   R0_CHECK(nblocks <= (size_t(1) << DIV_MAXLG), "poly_divide: polynomial too long");
-  DivPowers pw;
-  pw.z = z;
-  FpExt z8 = ext_pow(z, DIV_E);
-  FpExt cur = z8;
-  for (int s = 0; s < 8; s++) {
-    pw.zs[s] = cur;
-    cur = ext_mul(cur, cur);
+  R0_CHECK(njobs <= 65535, "poly_divide: too many jobs");
+  std::vector<DivPowers> pws(njobs);
+  std::vector<DivJob> jobs(njobs);
+  for (size_t j = 0; j < njobs; j++) {
+    DivPowers& pw = pws[j];
+    pw.z = zs[j];
+    FpExt z8 = ext_pow(zs[j], DIV_E);
+    FpExt cur = z8;
+    for (int s = 0; s < 8; s++) {
+      pw.zs[s] = cur;
+      cur = ext_mul(cur, cur);
+    }
+    // cur = z^(8 * 256) = z^SEG
+    for (int s = 0; s <= DIV_MAXLG; s++) {
+      pw.Z[s] = cur;
+      cur = ext_mul(cur, cur);
+    }
+    FpExt acc = ext_one();
+    for (int t = DIV_B - 1; t >= 0; t--) {
+      pw.zt[t] = acc;
+      acc = ext_mul(acc, z8);
+    }
+    jobs[j] = DivJob{(FpExt*)polys[j], (FpExt*)remainders_dev[j]};
   }
-  // cur = z^(8 * 256) = z^SEG
-  for (int s = 0; s <= DIV_MAXLG; s++) {
-    pw.Z[s] = cur;
-    cur = ext_mul(cur, cur);
-  }
-  FpExt acc = ext_one();
-  for (int t = DIV_B - 1; t >= 0; t--) {
-    pw.zt[t] = acc;
-    acc = ext_mul(acc, z8);
-  }
-  Scratch d_pw(c, &pw, sizeof(pw));
-  Scratch totals(c, nblocks * sizeof(FpExt));
-  Scratch carry(c, nblocks * sizeof(FpExt));
-  k_div_block_totals<<<(unsigned)nblocks, DIV_B, 0, c->stream>>>(totals.as<FpExt>(), (const FpExt*)poly, n, d_pw.as<DivPowers>());
-  k_div_block_carries<<<1, 1024, 0, c->stream>>>(carry.as<FpExt>(), totals.as<FpExt>(), nblocks, d_pw.as<DivPowers>());
-  k_div_quotient<<<(unsigned)nblocks, DIV_B, 0, c->stream>>>((FpExt*)poly, n, carry.as<FpExt>(), d_pw.as<DivPowers>(),
-                                                             (FpExt*)remainder_dev);
+  Scratch d_pw(c, pws.data(), njobs * sizeof(DivPowers));
+  Scratch d_jobs(c, jobs.data(), njobs * sizeof(DivJob));
+  Scratch totals(c, njobs * nblocks * sizeof(FpExt));
+  Scratch carry(c, njobs * nblocks * sizeof(FpExt));
+  const dim3 grid((unsigned)nblocks, (unsigned)njobs);
+  k_div_block_totals<<<grid, DIV_B, 0, c->stream>>>(totals.as<FpExt>(), d_jobs.as<DivJob>(), n, d_pw.as<DivPowers>());
+  k_div_block_carries<<<(unsigned)njobs, 1024, 0, c->stream>>>(carry.as<FpExt>(), totals.as<FpExt>(), nblocks,
+                                                                d_pw.as<DivPowers>());
+  k_div_quotient<<<grid, DIV_B, 0, c->stream>>>(d_jobs.as<DivJob>(), n, carry.as<FpExt>(), d_pw.as<DivPowers>());
   count_launch(c, 3);
   R0_CUDA(cudaGetLastError());
+}
+
+void r0_poly_divide(Ctx* c, uint32_t* poly, size_t n, const FpExt& z, uint32_t* remainder_dev) {
+  r0_poly_divide_batch(c, &poly, &z, &remainder_dev, 1, n);
 }
 
 // ---- batched query openings (product driver) ------------------------------------------------------------------
