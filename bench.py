@@ -75,6 +75,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout must carry exactly one line, the JSON. Native libraries write there too (NCCL prints its version banner
+    with printf when NCCL_DEBUG is VERSION or WARN), so fd 1 points at stderr until emit() prints the result."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args, rank, world):
     """CPU prover on the host cores (rank 0 only). Each step proves one bounded-size segment."""
     if rank != 0:
@@ -104,7 +124,7 @@ def run_reference(args, rank, world):
                                  "prover cost per cycle is flat in po2 up to the log factor)" % (po2, args.po2), "hash": "poseidon2"},
             "cpu_baseline": {"value": value, "unit": "cycles/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -119,6 +139,7 @@ def main():
     ap.add_argument("--hash", default="poseidon2", choices=["poseidon2", "sha-256"],
                     help="hash suite (the reference's default for rv32im segments is poseidon2)")
     args = ap.parse_args()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -134,8 +155,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the B200 backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries the one JSON line only: NCCL's own banner / debug output (NCCL_DEBUG set by the box) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hal = B200Hal(local_rank, args.hash)
     prover = SegmentProver(hal)
@@ -297,7 +316,7 @@ def main():
                 "gpu_launches": int(launches), "roofline": roofline, "int32_roofline": int32, "cpu_baseline": cpu_baseline,
                 "phase_ms_per_step": phase_ms, "phase_alg_GBps": phase_gbs, "clocks": sampler.result(),
                 "seal_words": int(len(seal)), "peak_device_bytes": hal.bytes_peak()}
-        print(json.dumps(line), flush=True)
+        emit(line)
     hal.close()
     if world > 1:
         dist.destroy_process_group()
