@@ -4,7 +4,8 @@
 
 void r0_ntt_init_tables(r0::Ctx* c);
 void r0_ntt_free_tables(r0::Ctx* c);
-void r0_ntt_interpolate(r0::Ctx* c, uint32_t* io, size_t count, int k, bool zk, size_t cols_per_launch);
+void r0_ntt_interpolate(r0::Ctx* c, uint32_t* io, size_t count, int k, bool zk, size_t cols_per_launch,
+                        const uint32_t* src = nullptr);
 void r0_ntt_expand_evaluate(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t count, int k, int eb,
                             size_t cols_per_launch);
 void r0_bit_reverse(r0::Ctx* c, uint32_t* io, size_t count, int k);

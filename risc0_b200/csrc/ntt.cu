@@ -588,8 +588,11 @@ __device__ __forceinline__ void strided_step(const NttArgs& a, uint32_t* s, uint
     uint32_t* sp = s + padh(base) * T + l;
     uint32_t* gp = io + ((size_t)base << a.k2) + l;
     if (FROM_GLOBAL) {
+      // the inverse transform may read its input from another buffer (a.in) and leave it untouched; io - a.out is the
+      // element offset of this block's tile
+      const uint32_t* rp = (DIR == 0) ? a.in + (gp - a.out) : gp;
 #pragma unroll
-      for (int j = 0; j < (1 << A); ++j) v[j] = gp[(size_t)(j << S) << a.k2];
+      for (int j = 0; j < (1 << A); ++j) v[j] = rp[(size_t)(j << S) << a.k2];
     } else {
 #pragma unroll
       for (int j = 0; j < (1 << A); ++j) v[j] = sp[j * PS];
@@ -920,11 +923,18 @@ static void dispatch_strided(Ctx* c, const NttArgs& a, size_t ncols) {
   count_launch(c);
 }
 
-// io: count rows of 2^k, natural order in, bit-reversed coefficients out, scaled by 2^-k; zk: also * 3^brev(i)
-void r0_ntt_interpolate(Ctx* c, uint32_t* io, size_t count, int k, bool zk, size_t cols_per_launch) {
+// io: count rows of 2^k, natural order in, bit-reversed coefficients out, scaled by 2^-k; zk: also * 3^brev(i).
+// src (optional): read the evaluations from there instead of io (out-of-place: saves the caller's copy)
+void r0_ntt_interpolate(Ctx* c, uint32_t* io, size_t count, int k, bool zk, size_t cols_per_launch,
+                        const uint32_t* src) {
+  if (!src) src = io;
   R0_CHECK(k >= 0 && k <= MAX_LG, "batch_interpolate_ntt: size out of range");
   PhaseScope ph(c, zk ? "ntt_interpolate_zk" : "ntt_interpolate", 8.0 * (double)count * (double)(size_t(1) << k));
-  if (count == 0 || k == 0) return;  // a 1-point transform is the identity (n^-1 = 3^0 = 1)
+  if (count == 0) return;
+  if (k == 0) {  // a 1-point transform is the identity (n^-1 = 3^0 = 1)
+    if (src != io) R0_CUDA(cudaMemcpyAsync(io, src, count * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return;
+  }
   NttArgs a{};
   a.k = k;
   split(k, a.k1, a.k2);
@@ -940,10 +950,13 @@ void r0_ntt_interpolate(Ctx* c, uint32_t* io, size_t count, int k, bool zk, size
   if (group > 65535) group = 65535;
   for (size_t c0 = 0; c0 < count; c0 += group) {
     size_t nc = count - c0 < group ? count - c0 : group;
-    a.in = io + (c0 << k);
+    a.in = src + (c0 << k);   // read by the first pass only; everything after it works in place on `io`
     a.out = io + (c0 << k);
     a.tiles_total = nc << a.k1;
-    if (a.k1) dispatch_strided<0>(c, a, nc);
+    if (a.k1) {
+      dispatch_strided<0>(c, a, nc);
+      a.in = a.out;
+    }
     dispatch_inv_contig(c, a);
   }
   R0_CUDA(cudaGetLastError());

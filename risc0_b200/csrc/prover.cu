@@ -304,8 +304,8 @@ class SegmentProver {
     if (witness_dev) {
       pg.count = count;
       pg.coeffs = DevBuf(c_, count * cycles_);
-      r0_eltwise_copy(c_, pg.coeffs.p, witness_dev, count * cycles_);
-      r0_ntt_interpolate(c_, pg.coeffs.p, count, (int)po2_, /*zk=*/true, 0);
+      // make_coeffs' copy (poly_group.rs:63-83) is folded into the transform: it reads the witness and writes coeffs
+      r0_ntt_interpolate(c_, pg.coeffs.p, count, (int)po2_, /*zk=*/true, 0, witness_dev);
     } else {
       const size_t chunk = upload_chunk_cols();
       size_t j = 0;

@@ -97,6 +97,9 @@ def test_prove_segment_bit_exact(hal, po2):
     d = [hal.copy_from_elem("w", x) for x in (code, data, accum)]
     seal2, _, _ = SegmentProver(hal).prove(po2, d[0], d[1], d[2], glob)
     assert np.array_equal(seal2, want_seal)
+    # ... and is left untouched (the iNTT reads it out of place into the coefficient buffer)
+    for buf, host in zip(d, (code, data, accum)):
+        assert np.array_equal(buf.view(), host)
 
 
 def test_prove_segment_invalid_globals_zeroed(hal):
