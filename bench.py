@@ -267,7 +267,7 @@ def main():
                 "share_of_step": t["ms"] / (ms if world == 1 else ms),
                 "note": "achieved = algorithmic bytes ((4*315+16) B per domain point for eval_check, 4*cols+32 B per row for "
                         "hash_rows) / summed device time of the family. Both are INT32-bound, not HBM-bound (Poseidon2: 1356 "
-                        "modmul per permutation; eval_check: ~270 k instructions per point, alu pipe at 86 % of its ceiling), so "
+                        "modmul per permutation; eval_check: ~270 k instructions per point, fma-heavy pipe at 59 % of the ceiling of its own multiply count, see int32_roofline), so "
                         "the HBM fraction is low by construction; eval_check's DRAM traffic is ~20x algorithmic because every "
                         "part kernel re-reads the tap columns it needs. See DESIGN.md 3.3/3.4 and profiles/."}
     phase_ms = {k: round(v["ms"] / args.steps, 4) for k, v in sorted(phases.items(), key=lambda kv: -kv[1]["ms"])}
