@@ -22,7 +22,7 @@
 //    splitting the batch into column groups any more - that only cost tail waves (R0_NTT_L2_MB re-enables it).
 #include "ctx.h"
 
-// Compile-time tuning knobs (tools/sweep_ntt.sh builds variants; the defaults are the measured best).
+// Compile-time tuning knobs (tools/sweep_ntt.py builds and times variants; the defaults are the measured best).
 #ifndef R0_NTT_THREADS
 #define R0_NTT_THREADS 256
 #endif
