@@ -276,6 +276,7 @@ def partition(dag, uses, nparts, limit=None):
 NINV = 0x77FFFFFF            # -P^-1 mod 2^32
 PINV = 0x88000001            # P^-1 mod 2^32
 MONT_ONE = R
+PLAIN_ADD = os.environ.get("EVAL_PLAIN_ADD", "1") == "1"
 RINV = pow(R, -1, P)
 NBETA_M = mont(P - 11)
 
@@ -532,13 +533,18 @@ def flatten_sums(S, outs):
                 if pend:
                     stack.extend(pend)
                     continue
-                terms = []
+                terms, plain = [], []
                 for sg, x in lv:
                     kx = S.nodes[x]
                     if kx[0] == "*":      # a product costs one MAC wherever it is used: never worth a register
                         prods = [(memo[kx[1]], memo[kx[2]])]
                     elif uses[x] == 1 and kx[0] == "d":
                         prods = [(memo[a], memo[b]) for a, b in kx[1]]
+                    elif PLAIN_ADD:
+                        # a plain addend joins AFTER the reduction (IADD3 + VIADDMNMX on the alu pipe) instead of
+                        # entering the dot product as x * 1 (an IMAD.WIDE on the fma-heavy pipe, the saturated one)
+                        plain.append((sg, memo[x]))
+                        continue
                     else:
                         prods = [(memo[x], T.imm(MONT_ONE))]
                     for a, b in prods:
@@ -551,7 +557,12 @@ def flatten_sums(S, outs):
                             else:
                                 b = T.add_node(("N", b))   # lazy negation P - b (may equal P; fine inside a product)
                         terms.append((a, b))
-                r = T.add_node(("d", tuple(terms)))
+                r = T.add_node(("d", tuple(terms))) if terms else None
+                for sg, v in plain:
+                    if r is None:
+                        r = v if sg > 0 else T.neg(v)
+                    else:
+                        r = T.add(r, v) if sg > 0 else T.sub(r, v)
             else:
                 ops = S.operands(cur)
                 pend = [x for x in ops if x not in memo]
@@ -624,6 +635,7 @@ class Ptx:
         self.split = int(os.environ.get("EVAL_SPLIT", "1600"))
         self.last_fence = 0
         self.use_bar = os.environ.get("EVAL_BAR", "0") == "1"
+        self.first_wide = os.environ.get("EVAL_FIRST_WIDE", "1") == "1"
         self.bases = {}
 
     def t(self):
@@ -680,7 +692,13 @@ class Ptx:
         """(lo, hi) += a * b as the carry-chained 32-bit pair that ptxas folds into ONE IMAD.WIDE with a 64-bit
         accumulator operand (a mad.wide chain is instead re-associated into IMAD.WIDE + IADD3/IADD3.X trees, which
         puts ~1.5 extra instructions per product on the half-rate alu pipe)"""
-        if first:
+        if first and self.first_wide:
+            # one IMAD.WIDE for certain: ptxas leaves ~2/3 of the mul.lo / mul.hi pairs as IMAD + IMAD.HI (6 fma-pipe
+            # cycles instead of 4)
+            w = self.w()
+            self.emit("mul.wide.u32 %s, %s, %s;" % (w, a, b))
+            self.emit("mov.b64 {%s, %s}, %s;" % (lo, hi, w))
+        elif first:
             self.emit("mul.lo.u32 %s, %s, %s;" % (lo, a, b))
             self.emit("mul.hi.u32 %s, %s, %s;" % (hi, a, b))
         else:
