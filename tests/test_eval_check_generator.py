@@ -17,25 +17,17 @@ P = O.P
 pytestmark = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
 
 
-def test_scalar_lowering_matches_reference_poly_fp():
+def _setup(po2=5):
+    """random evaluated groups + the constant block exactly as the launcher fills it, and the reference's answer"""
     dag = G.load_ir(os.path.join(ROOT, "risc0_b200", "circuits", "rv32im.ir.json.gz"))
     npm = 1 + max(k[1] for k in dag.nodes if k[0] == "pm")
     assert npm == 458
     lay = G.Layout(npm, 90, 36)
-    uses = [0] * len(dag.nodes)
-    for k in dag.nodes:
-        if k[0] in "+-*":
-            uses[k[1]] += 1
-            uses[k[2]] += 1
-    parts = G.partition(dag, uses, 8)
-    po2 = 5
     n, domain = 1 << po2, 4 << po2
     rng = np.random.default_rng(11)
     accum, data = O.rand_elems(rng, 103 * domain), O.rand_elems(rng, 211 * domain)
     mix, out, poly_mix = O.rand_elems(rng, 36), O.rand_elems(rng, 90), O.rand_ext(rng)
     want = O.rv32im_eval_check(accum, data, mix, out, poly_mix, po2).reshape(4, domain)
-
-    # constant block exactly as the launcher fills it
     L = O.lib()
     tables = open(os.path.join(ROOT, "risc0_b200", "csrc", "tables", "circuit_rv32im.h")).read()
     pows = [int(x) for x in tables.split("RV32IM_POLY_MIX_POWERS[458] = {")[1].split("}")[0].replace("u", "").split(",") if x.strip()]
@@ -60,6 +52,58 @@ def test_scalar_lowering_matches_reference_poly_fp():
     for _ in range(4):
         inv_y.append(L.orc_fp_inv(L.orc_fp_sub(L.orc_fp_mul(three_n, cur), int(O.encode(1)))))
         cur = L.orc_fp_mul(cur, w4)
+    return dict(dag=dag, lay=lay, domain=domain, accum=accum, data=data, want=want, consts=consts, inv_y=inv_y)
+
+
+def test_emitted_ptx_matches_reference_poly_fp():
+    """the PTX text that ptxas assembles (csrc/gen/eval_check_rv32im_p*.ptx), run one thread at a time by
+    tools/ptx_interp.py, gives the reference's check polynomial word for word"""
+    import glob
+    import subprocess
+    from ptx_interp import Kernel, Memory
+    gen_dir = os.path.join(ROOT, "risc0_b200", "csrc", "gen")
+    files = glob.glob(os.path.join(gen_dir, "eval_check_rv32im_p*.ptx"))
+    if not files:
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_eval_check.py"), "rv32im", "--from-ir"],
+                              stdout=subprocess.DEVNULL)
+        files = glob.glob(os.path.join(gen_dir, "eval_check_rv32im_p*.ptx"))
+    files.sort(key=lambda f: int(f.rsplit("_p", 1)[1][:-4]))
+    s = _setup()
+    lay, domain = s["lay"], s["domain"]
+    cst = bytearray(lay.size)
+    for off, v in s["consts"].items():
+        cst[off:off + 4] = int(v).to_bytes(4, "little")
+    for r in range(4):
+        cst[lay.inv_y + 4 * r:lay.inv_y + 4 * r + 4] = int(s["inv_y"][r]).to_bytes(4, "little")
+    check = np.full(4 * domain, 0xDEADBEEF, dtype=np.uint32)   # part 0 must overwrite, not accumulate
+    bases = {"p_check": 1 << 40, "p_accum": 2 << 40, "p_code": 3 << 40, "p_data": 4 << 40}
+    mem = Memory({bases["p_check"]: check, bases["p_accum"]: s["accum"].copy(),
+                  bases["p_code"]: np.zeros(domain, dtype=np.uint32), bases["p_data"]: s["data"].copy()})
+    points = (0, 3, 77, domain - 1)
+    for j, f in enumerate(files):
+        k = Kernel(open(f).read())
+        assert [name for name, _ in k.params] == ["p_check", "p_accum", "p_code", "p_data", "p_domain", "p_first", "p_i0", "p_cst"]
+        for i in points:
+            params = dict(bases, p_domain=domain, p_first=1 if j == 0 else 0, p_i0=0, p_cst=bytes(cst))
+            k.run(params, mem, tid=i, ctaid=0, ntid=128)
+    for i in points:
+        assert [int(check[c * domain + i]) for c in range(4)] == [int(x) for x in s["want"][:, i]], i
+    # a thread beyond the domain leaves memory alone
+    before = check.copy()
+    Kernel(open(files[0]).read()).run(dict(bases, p_domain=domain, p_first=1, p_i0=0, p_cst=bytes(cst)), mem, tid=5, ctaid=1, ntid=128)
+    assert np.array_equal(check, before)
+
+
+def test_scalar_lowering_matches_reference_poly_fp():
+    s = _setup()
+    dag, lay, domain, accum, data, want, consts, inv_y = (s[k] for k in ("dag", "lay", "domain", "accum", "data", "want", "consts", "inv_y"))
+    L = O.lib()
+    uses = [0] * len(dag.nodes)
+    for k in dag.nodes:
+        if k[0] in "+-*":
+            uses[k[1]] += 1
+            uses[k[2]] += 1
+    parts = G.partition(dag, uses, 8)
 
     lowered = []
     for part in parts:
