@@ -22,7 +22,7 @@ def _setup(po2=5):
     dag = G.load_ir(os.path.join(ROOT, "risc0_b200", "circuits", "rv32im.ir.json.gz"))
     npm = 1 + max(k[1] for k in dag.nodes if k[0] == "pm")
     assert npm == 458
-    lay = G.Layout(npm, 90, 36)
+    lay = G.Layout(npm, 90, 36, 211)   # 211 = widest group (data); only used by the optional address table
     n, domain = 1 << po2, 4 << po2
     rng = np.random.default_rng(11)
     accum, data = O.rand_elems(rng, 103 * domain), O.rand_elems(rng, 211 * domain)
@@ -75,6 +75,8 @@ def test_emitted_ptx_matches_reference_poly_fp():
         cst[off:off + 4] = int(v).to_bytes(4, "little")
     for r in range(4):
         cst[lay.inv_y + 4 * r:lay.inv_y + 4 * r + 4] = int(s["inv_y"][r]).to_bytes(4, "little")
+    for q in range(lay.ncols):   # EVAL_ADDR_TABLE variant: byte offsets of the columns
+        cst[lay.coloff + 8 * q:lay.coloff + 8 * q + 8] = (q * domain * 4).to_bytes(8, "little")
     check = np.full(4 * domain, 0xDEADBEEF, dtype=np.uint32)   # part 0 must overwrite, not accumulate
     bases = {"p_check": 1 << 40, "p_accum": 2 << 40, "p_code": 3 << 40, "p_data": 4 << 40}
     mem = Memory({bases["p_check"]: check, bases["p_accum"]: s["accum"].copy(),
@@ -83,6 +85,7 @@ def test_emitted_ptx_matches_reference_poly_fp():
     for j, f in enumerate(files):
         k = Kernel(open(f).read())
         assert [name for name, _ in k.params] == ["p_check", "p_accum", "p_code", "p_data", "p_domain", "p_first", "p_i0", "p_cst"]
+        assert k.params[-1][1] == ("b8", lay.size)
         for i in points:
             params = dict(bases, p_domain=domain, p_first=1 if j == 0 else 0, p_i0=0, p_cst=bytes(cst))
             k.run(params, mem, tid=i, ctaid=0, ntid=128)

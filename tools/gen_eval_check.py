@@ -277,6 +277,7 @@ NINV = 0x77FFFFFF            # -P^-1 mod 2^32
 PINV = 0x88000001            # P^-1 mod 2^32
 MONT_ONE = R
 PLAIN_ADD = os.environ.get("EVAL_PLAIN_ADD", "1") == "1"
+ADDR_TABLE = os.environ.get("EVAL_ADDR_TABLE", "0") == "1"
 RINV = pow(R, -1, P)
 NBETA_M = mont(P - 11)
 
@@ -372,7 +373,7 @@ class Scalars:
 class Layout:
     """byte offsets inside the kernel's constant parameter block"""
 
-    def __init__(self, npm, n_global, n_mix):
+    def __init__(self, npm, n_global, n_mix, ncols=0):
         self.pm = 0
         self.npm = 16 * npm
         self.glob = 32 * npm
@@ -380,6 +381,12 @@ class Layout:
         self.inv_y = self.mix + 4 * n_mix
         self.size = self.inv_y + 16
         self.n = npm
+        # EVAL_ADDR_TABLE: byte offsets col * stride of the tap columns as 64-bit constants, so that a tap address is
+        # base + c[...] (IADD3 + IADD3.X with constant-bank operands) instead of an IMAD.WIDE on the fma-heavy pipe
+        self.ncols = ncols if ADDR_TABLE else 0
+        if self.ncols:
+            self.coloff = (self.size + 7) & ~7
+            self.size = self.coloff + 8 * self.ncols
 
 
 def lower(dag, terms, lay):
@@ -832,7 +839,12 @@ class Ptx:
                 base = "%%b_%s_%d" % (k[1], k[3])
                 self.bases[(k[1], k[3])] = base
                 a = self.w()
-                self.emit("mad.wide.u32 %s, %%stride, %d, %s;" % (a, k[2], base))
+                if self.lay.ncols:
+                    o = self.w()
+                    self.emit("ld.param.u64 %s, [p_cst+%d];" % (o, self.lay.coloff + 8 * k[2]))
+                    self.emit("add.u64 %s, %s, %s;" % (a, base, o))
+                else:
+                    self.emit("mad.wide.u32 %s, %%stride, %d, %s;" % (a, k[2], base))
                 self.emit("ld.global.nc.u32 %s, [%s];" % (reg, a))
                 st = [reg, self.pos]
                 self.tap_state[i] = st
@@ -1071,7 +1083,7 @@ struct Consts {
   uint32_t global[%(n_global)d];
   uint32_t mix[%(n_mix)d];
   uint32_t inv_y[4];
-};
+%(coloff_decl)s};
 static_assert(sizeof(Consts) == %(cst_size)d, "constant block layout differs from the generator's");
 
 constexpr int kParts = %(nparts)d;
@@ -1136,7 +1148,7 @@ void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, cons
     k.inv_y[r] = fp_inv(fp_sub(fp_mul(three_n, cur), MONT_ONE));
     cur = fp_mul(cur, R0_ROU_FWD_MONT[2]);
   }
-  const unsigned threads = %(threads)d;
+%(coloff_fill)s  const unsigned threads = %(threads)d;
   // Optional point tiles (EVAL_TILE_LG at generation time; default = whole domain): running all parts over a tile of
   // 2^16 points keeps its tap columns (83 MB for rv32im) in L2 for the later parts and cuts DRAM traffic ~15x, but the
   // 512-block launches it needs run at well under full occupancy: measured 26.1 ms per 2^20 points against 16.2 ms
@@ -1178,7 +1190,7 @@ def main():
         dag = ir.build_dag(fns, arg_names=cfg["arg_names"])
         save_ir(dag, ir_path)
     npm = 1 + max(k[1] for k in dag.nodes if k[0] == "pm")
-    lay = Layout(npm, cfg["n_global"], cfg["n_mix"])
+    lay = Layout(npm, cfg["n_global"], cfg["n_mix"], max(cfg["cols"].values()))
     uses = [0] * len(dag.nodes)
     for k in dag.nodes:
         if k[0] in "+-*":
@@ -1215,7 +1227,9 @@ def main():
     params = dict(name=name, NAME=name.upper(), nparts=len(parts), npm=npm, n_global=cfg["n_global"], n_mix=cfg["n_mix"],
                   cst_size=lay.size, threads=threads, ncols=sum(cfg["cols"].values()),
                   tile_lg=int(os.environ.get("EVAL_TILE_LG", "30")), externs="\n".join(externs), images=", ".join(images),
-                  names=", ".join(names), part_names=", ".join('"eval_check_p%d"' % j for j in range(len(parts))))
+                  names=", ".join(names), part_names=", ".join('"eval_check_p%d"' % j for j in range(len(parts))),
+                  coloff_decl=("  uint64_t col_off[%d];  // byte offset of column q inside an evaluated group\n" % lay.ncols) if lay.ncols else "",
+                  coloff_fill=("  for (int q = 0; q < %d; q++) k.col_off[q] = (uint64_t)q * domain * 4;\n" % lay.ncols) if lay.ncols else "")
     with open(os.path.join(gen_dir, "eval_check_%s.cu" % name), "w") as f:
         f.write(LAUNCHER % params)
     # per-point operation counts of the emitted kernels (bench.py's INT32 roofline reads them)
