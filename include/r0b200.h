@@ -33,6 +33,7 @@ typedef struct r0b200_ctx r0b200_ctx;
 typedef const char* r0b200_err;
 
 enum { R0B200_HASH_POSEIDON2 = 0, R0B200_HASH_SHA256 = 1 };
+enum { R0B200_CIRCUIT_RV32IM = 0, R0B200_CIRCUIT_RECURSION = 1 };
 
 /* ---- context (CudaHal::new_from_hash, hal/cuda.rs:397-421; sppark_init, supra/ntt.cu:4-32) ---- */
 r0b200_err r0b200_create(int device, r0b200_ctx** out);
@@ -139,18 +140,44 @@ r0b200_err r0b200_eval_check_recursion(r0b200_ctx* ctx, uint32_t* check, const u
                                        const uint32_t* poly_mix_host, uint32_t po2);
 
 /* ---- whole segment (the Hal's caller on the hot path) ---- */
-/* prove_core's prove_inner block for a committed rv32im witness (rv32im/src/prove/hal/mod.rs:171-222 ->
- * zkp/src/prove/prover.rs:81-393 -> prove/fri.rs:77-126): commits code (1 x N), data (211 x N), accum (103 x N),
- * N = 2^po2, runs eval_check, DEEP and FRI, and writes the seal (u32 words, the reference's seal format) to host
- * memory. code/data/accum are column-major witness matrices, device pointers unless witness_on_host != 0 (then they
- * are copied with stream-ordered H2D copies first - pinned memory makes those asynchronous). global_host: 90 words.
- * Optional outputs (may be NULL): every committed Merkle root in commit order, and the 50 drawn query positions. */
+/* prove_core's prove_inner block (rv32im/src/prove/hal/mod.rs:171-222 -> zkp/src/prove/prover.rs:81-393 ->
+ * prove/fri.rs:77-126), split where the protocol splits it: the accum matrix is computed FROM the mix values the
+ * transcript yields after code and data have been committed (hal/mod.rs:209-217: commit_group(CODE), commit_group(DATA),
+ * mix = MIX_SIZE x iop.random_elem(), witgen.accum(.., &mix), commit_group(ACCUM), finalize), so a caller cannot hand
+ * all three matrices over at once.
+ *
+ *   r0b200_prove_begin : version word, info + header commits, code (1 x N) and data (211 x N) groups, N = 2^po2; draws
+ *                        the mix and returns it (36 words rv32im, 20 recursion) together with a proof handle.
+ *   r0b200_prove_finish: commits accum (103 x N), runs eval_check, DEEP and FRI, writes the seal (u32 words, the
+ *                        reference's seal format) to host memory and releases the handle (also on failure).
+ *   r0b200_prove_abort : releases a handle without finishing.
+ *
+ * code/data/accum are column-major witness matrices: device pointers, or host pointers when the *_on_host flag is set
+ * (copied with stream-ordered H2D copies on the context's copy stream, chunk by chunk, overlapped with compute; pinned
+ * memory makes them asynchronous; they must stay valid until the call that consumes them returns). A device-resident
+ * witness is left untouched (the first NTT pass reads it out of place), so the data matrix can still be read by the
+ * accum step between begin and finish. `uploaded` (may be NULL) is a witness from r0b200_witness_upload; when given,
+ * code/data/po2 are taken from it. global_host: 90 words (rv32im) / 32 (recursion).
+ * Optional outputs of finish (may be NULL): every committed Merkle root in commit order, and the 50 query positions. */
+typedef struct r0b200_proof r0b200_proof;
+typedef struct r0b200_witness r0b200_witness;
+r0b200_err r0b200_prove_begin(r0b200_ctx* ctx, int circuit, int hash, uint32_t po2, const uint32_t* code,
+                              const uint32_t* data, int witness_on_host, r0b200_witness* uploaded,
+                              const uint32_t* global_host, uint32_t* mix_out_host, size_t mix_cap, r0b200_proof** out);
+r0b200_err r0b200_prove_finish(r0b200_proof* proof, const uint32_t* accum, int accum_on_host, uint32_t* seal_out_host,
+                               size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap,
+                               size_t* nroots, uint32_t* query_pos_out_host);
+void r0b200_prove_abort(r0b200_proof* proof);
+
+/* One-call form = prove_begin + prove_finish with an accum matrix that was fixed BEFORE the mix was drawn. Only
+ * meaningful for witnesses whose accum does not depend on the mix (the synthetic witnesses of the parity tests and
+ * micro-benchmarks); a real prove_core must use the two-phase form above. */
 r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* code, const uint32_t* data,
                                const uint32_t* accum, int witness_on_host, const uint32_t* global_host,
                                uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
                                size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host);
 
-/* RecursionProverImpl::prove's prove block (recursion/src/prove/mod.rs:179-224) for a committed witness: ctrl
+/* RecursionProverImpl::prove's prove block (recursion/src/prove/mod.rs:179-224), one-call form (same caveat): ctrl
  * (23 x N), data (128 x N), accum (12 x N), global_host 32 words; lift / join / resolve programs all have this shape
  * (po2 = 18 by default). No seal version word. */
 r0b200_err r0b200_prove_recursion(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* ctrl, const uint32_t* data,
@@ -163,8 +190,9 @@ r0b200_err r0b200_prove_recursion(r0b200_ctx* ctx, int hash, uint32_t po2, const
  * proved, segment s+1 is prepared. r0b200_witness_upload() enqueues the host->device copy of a witness (circuit 0 =
  * rv32im, 1 = recursion; column-major host matrices, pinned memory makes the copies asynchronous) on the context's
  * copy stream and returns at once; r0b200_prove_uploaded() consumes it (the handle's buffers pass to the proof; free
- * the handle afterwards). Uploading s+1 before proving s hides the PCIe transfer behind compute. */
-typedef struct r0b200_witness r0b200_witness;
+ * the handle afterwards). Uploading s+1 before proving s hides the PCIe transfer behind compute. accum_host may be
+ * NULL (the normal case: accum does not exist before prove_begin has drawn the mix); the handle is then consumed by
+ * r0b200_prove_begin(.., uploaded, ..) and accum goes to r0b200_prove_finish. */
 r0b200_err r0b200_witness_upload(r0b200_ctx* ctx, int circuit, uint32_t po2, const uint32_t* code_host,
                                  const uint32_t* data_host, const uint32_t* accum_host, r0b200_witness** out);
 void r0b200_witness_free(r0b200_witness* witness);

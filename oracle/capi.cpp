@@ -252,6 +252,20 @@ extern "C" const char* orc_combos_divide(uint32_t* combos, uint64_t nchunks, con
   if (!combos_divide((FpExt*)combos, ch, cycles)) throw std::runtime_error("combos_divide: nonzero remainder");
   ORC_CATCH
 }
+// core/poly.rs:81-89 poly_divide: in-place synthetic division by (x - z); the remainder goes to rem_out (4 words)
+extern "C" void orc_poly_divide(uint32_t* poly, uint64_t n, const uint32_t* z, uint32_t* rem_out) {
+  FpExt rem = poly_divide((FpExt*)poly, n, ext_of(z));
+  for (size_t k = 0; k < EXT_SIZE; k++) rem_out[k] = rem.e[k].v;
+}
+// map_pow(poly_mix, POLY_MIX_POWERS) as rv32im/src/prove/hal/cuda.rs:207-211 hands it to the FFI (458 x 4 words)
+extern "C" uint32_t orc_rv32im_poly_mix_pows(const uint32_t* poly_mix, uint32_t* out) {
+  FpExt pm = ext_of(poly_mix);
+  for (size_t i = 0; i < RV32IM_NUM_POLY_MIX_POWERS; i++) {
+    FpExt v = pm.pow(RV32IM_POLY_MIX_POWERS[i]);
+    for (size_t k = 0; k < EXT_SIZE; k++) out[4 * i + k] = v.e[k].v;
+  }
+  return RV32IM_NUM_POLY_MIX_POWERS;
+}
 extern "C" void orc_poly_interpolate(uint32_t* out, const uint32_t* x, const uint32_t* fx, uint64_t size) {
   poly_interpolate((FpExt*)out, size, (const FpExt*)x, (const FpExt*)fx, size);
 }
@@ -279,10 +293,13 @@ static const char* finish(SealOut* so, uint32_t* seal_out, uint64_t seal_cap, ui
 // Restates SegmentProverImpl::prove_core's "prove_inner" block (rv32im/src/prove/hal/mod.rs:171-222) for a GIVEN
 // witness: code (1 x N), data (211 x N), accum (103 x N), global (90). The accum witness is an input (the synthetic
 // workload of SURVEY §8d), so the 36 drawn mix values only feed eval_check.
-extern "C" const char* orc_prove_rv32im(int hash_kind, uint32_t po2, const uint32_t* code, const uint32_t* data,
-                                        const uint32_t* accum, const uint32_t* global, uint32_t* seal_out,
-                                        uint64_t seal_cap, uint64_t* seal_len, uint32_t* roots_out, uint64_t roots_cap,
-                                        uint64_t* nroots, uint32_t* qpos_out) {
+// prove_core's prove_inner block (rv32im/src/prove/hal/mod.rs:171-222). mix_out (36 words, may be null) receives the
+// accum mix drawn after the code and data commits (:213); with accum == nullptr the function stops there - that is
+// what a caller sees between the two phases (the accum matrix is computed from that mix, :213-216).
+static const char* prove_rv32im_impl(int hash_kind, uint32_t po2, const uint32_t* code, const uint32_t* data,
+                                     const uint32_t* accum, const uint32_t* global, uint32_t* mix_out, uint32_t* seal_out,
+                                     uint64_t seal_cap, uint64_t* seal_len, uint32_t* roots_out, uint64_t roots_cap,
+                                     uint64_t* nroots, uint32_t* qpos_out) {
   ORC_TRY
   HashSuite suite = suite_of(hash_kind);
   TapSet taps = rv32im_taps();
@@ -310,6 +327,9 @@ extern "C" const char* orc_prove_rv32im(int hash_kind, uint32_t po2, const uint3
   prover.commit_group(2, (const Fp*)data, N * 211);
   std::vector<Fp> mix(RV32IM_MIX_SIZE);
   for (auto& m : mix) m = prover.iop.random_elem();
+  if (mix_out)
+    for (size_t i = 0; i < RV32IM_MIX_SIZE; i++) mix_out[i] = mix[i].v;
+  if (!accum) return nullptr;
   prover.commit_group(0, (const Fp*)accum, N * 103);
   EvalCheckFn ec = [&](Fp* check, const std::vector<const Fp*>& g, const std::vector<const Fp*>& globals, FpExt pm,
                        size_t p2, size_t steps) {
@@ -319,6 +339,20 @@ extern "C" const char* orc_prove_rv32im(int hash_kind, uint32_t po2, const uint3
   const char* e = finish(&so, seal_out, seal_cap, seal_len, roots_out, roots_cap, nroots, qpos_out);
   if (e) return e;
   ORC_CATCH
+}
+
+extern "C" const char* orc_prove_rv32im(int hash_kind, uint32_t po2, const uint32_t* code, const uint32_t* data,
+                                        const uint32_t* accum, const uint32_t* global, uint32_t* seal_out,
+                                        uint64_t seal_cap, uint64_t* seal_len, uint32_t* roots_out, uint64_t roots_cap,
+                                        uint64_t* nroots, uint32_t* qpos_out) {
+  return prove_rv32im_impl(hash_kind, po2, code, data, accum, global, nullptr, seal_out, seal_cap, seal_len, roots_out,
+                           roots_cap, nroots, qpos_out);
+}
+
+extern "C" const char* orc_prove_rv32im_mix(int hash_kind, uint32_t po2, const uint32_t* code, const uint32_t* data,
+                                            const uint32_t* global, uint32_t* mix_out) {
+  return prove_rv32im_impl(hash_kind, po2, code, data, nullptr, global, mix_out, nullptr, 0, nullptr, nullptr, 0, nullptr,
+                           nullptr);
 }
 
 // HelloCircuit in the verify_v3 protocol (no header, groups committed in tap order accum, code, data).

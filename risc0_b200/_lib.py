@@ -26,6 +26,16 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(r0b200_[a-z0-9_]+)\s*\(", text)))
 
 
+COMPAT_HEADER = os.path.join(HERE, "..", "include", "r0b200_compat.h")
+
+
+def compat_symbols():
+    """every function name declared in include/r0b200_compat.h (the reference's own FFI symbol table)"""
+    text = open(COMPAT_HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:risc0_zkp_cuda|risc0_circuit|sppark|supra)_[A-Za-z0-9_]+)\s*\(", text)))
+
+
 def load_library():
     global _lib
     if _lib is None:
@@ -40,6 +50,7 @@ def load_library():
         _lib.r0b200_destroy.restype = None
         _lib.r0b200_free_error.restype = None
         _lib.r0b200_witness_free.restype = None
+        _lib.r0b200_prove_abort.restype = None
         _lib.r0b200_launch_count.restype = C.c_uint64
         _lib.r0b200_bytes_peak.restype = C.c_uint64
         _lib.r0b200_stream.restype = C.c_void_p

@@ -99,7 +99,7 @@ def _compile(src, obj, verbose):
 def build(force=False, verbose=False, jobs=None):
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
-    generate()
+    generate(force)
     hdr_time = max(os.path.getmtime(h) for h in headers())
     todo, objs = [], []
     for src in sources():
@@ -109,10 +109,14 @@ def build(force=False, verbose=False, jobs=None):
             todo.append((src, obj))
     # generated PTX kernels -> cubins, embedded as read-only data (symbol r0_cubin_<file stem>)
     ptx_todo, cubins = [], []
+    # the ptxas flag set is part of the cubin staleness key
+    stamp = os.path.join(OBJ, "ptxas_flags.stamp")
+    flag_key = repr((PTXAS_OPT, PTXAS_EXTRA, SPILL_LIMIT))
+    flags_changed = not os.path.exists(stamp) or open(stamp).read() != flag_key
     for ptx in ptx_sources():
         cubin = os.path.join(OBJ, os.path.basename(ptx)[:-4] + ".cubin")
         cubins.append(cubin)
-        if force or not os.path.exists(cubin) or os.path.getmtime(cubin) < os.path.getmtime(ptx):
+        if force or flags_changed or not os.path.exists(cubin) or os.path.getmtime(cubin) < os.path.getmtime(ptx):
             ptx_todo.append((ptx, cubin))
     if (todo or ptx_todo) and os.path.exists(LIB):
         os.remove(LIB)   # never leave a stale library behind a failed rebuild
@@ -124,6 +128,8 @@ def build(force=False, verbose=False, jobs=None):
                 src, log = f.result()
                 if verbose:
                     sys.stderr.write("== %s\n%s" % (os.path.basename(src), log))
+    with open(stamp, "w") as f:
+        f.write(flag_key)
     if cubins:
         embed_s = os.path.join(OBJ, "embed_cubins.S")
         embed_o = os.path.join(OBJ, "embed_cubins.o")

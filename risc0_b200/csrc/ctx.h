@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "fp.cuh"
 
 namespace r0 {
@@ -55,6 +57,7 @@ struct Ctx {
   uint64_t launches = 0;       // kernels launched through this context (bench.py's gpu_launches)
   size_t bytes_allocated = 0;  // MemoryTracker analogue (hal/mod.rs:292-317)
   size_t bytes_peak = 0;
+  std::map<void*, size_t> alloc_sizes;  // r0b200_alloc'd blocks, so r0b200_free can decrement bytes_allocated
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   // optional per-phase device timing (r0b200_profile_begin / _end): event pairs recorded on `stream` around each op
   bool profiling = false;
@@ -89,6 +92,16 @@ struct PhaseScope {
   ~PhaseScope() {
     if (b) cudaEventRecord(b, c->stream);
   }
+};
+
+// NVTX range with the reference's scope! names (risc0/core/src/perf.rs:22-73: scope!(name) pushes an NVTX range for
+// the enclosing block), so nsys timelines of this backend line up with the reference's. Header-only NVTX3: a no-op
+// unless a profiler injects itself.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 inline void count_launch(Ctx* c, uint64_t n = 1) { c->launches += n; }

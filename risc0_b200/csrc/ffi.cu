@@ -146,13 +146,21 @@ r0b200_err r0b200_alloc(r0b200_ctx* ctx, size_t bytes, void** dptr) {
   CTX_BEGIN
   R0_CHECK(dptr != nullptr, "r0b200_alloc: null out pointer");
   R0_CUDA(cudaMallocAsync(dptr, bytes ? bytes : 16, ctx->stream));
+  ctx->alloc_sizes[*dptr] = bytes;
   ctx->bytes_allocated += bytes;
   if (ctx->bytes_allocated > ctx->bytes_peak) ctx->bytes_peak = ctx->bytes_allocated;
   R0_API_END
 }
 r0b200_err r0b200_free(r0b200_ctx* ctx, void* dptr) {
   CTX_BEGIN
-  if (dptr) R0_CUDA(cudaFreeAsync(dptr, ctx->stream));
+  if (dptr) {
+    auto it = ctx->alloc_sizes.find(dptr);
+    if (it != ctx->alloc_sizes.end()) {
+      ctx->bytes_allocated -= it->second;
+      ctx->alloc_sizes.erase(it);
+    }
+    R0_CUDA(cudaFreeAsync(dptr, ctx->stream));
+  }
   R0_API_END
 }
 r0b200_err r0b200_copy_h2d(r0b200_ctx* ctx, void* dst, const void* src_host, size_t bytes) {

@@ -14,6 +14,8 @@ void r0_poseidon2_init(r0::Ctx* c);
 void r0_p2_hash_rows(r0::Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols);
 void r0_p2_hash_fold(r0::Ctx* c, uint32_t* io, size_t in_size, size_t out_size);
 void r0_p2_merkle_fold_all(r0::Ctx* c, uint32_t* nodes, size_t leaves);
+void r0_p2_fold_pairs(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t n);
+void r0_sha_fold_pairs(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t n);
 void r0_sha_hash_rows(r0::Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols);
 void r0_sha_hash_fold(r0::Ctx* c, uint32_t* io, size_t in_size, size_t out_size);
 
@@ -31,6 +33,12 @@ void r0_batch_evaluate_any(r0::Ctx* c, const uint32_t* coeffs, size_t n, const u
 void r0_gather_sample(r0::Ctx* c, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride);
 void r0_scatter(r0::Ctx* c, uint32_t* into, const uint32_t* index_host, size_t index_len, const uint32_t* offsets_host,
                 const uint32_t* values_host);
+void r0_scatter_dev(r0::Ctx* c, uint32_t* into, const uint32_t* index_dev, size_t count, const uint32_t* offsets_dev,
+                    const uint32_t* values_dev);
+void r0_copy_region_dev(r0::Ctx* c, uint32_t* into, const uint32_t* from_dev, size_t from_rows, size_t from_cols,
+                        size_t from_offset, size_t from_stride, size_t into_offset, size_t into_stride);
+void r0_expand_zero_interleave(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t n_in, int bits);
+void r0_eltwise_mul_factor(r0::Ctx* c, uint32_t* io, uint32_t factor, size_t n);
 void r0_copy_elem_slice(r0::Ctx* c, uint32_t* into, const uint32_t* from_host, size_t from_rows, size_t from_cols,
                         size_t from_offset, size_t from_stride, size_t into_offset, size_t into_stride);
 void r0_prefix_products(r0::Ctx* c, uint32_t* io, size_t n);

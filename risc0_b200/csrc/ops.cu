@@ -29,6 +29,10 @@ static inline unsigned grid_for(const Ctx* c, size_t n, int block = 256, int wav
 __global__ void k_add(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) {
   GRID_STRIDE(i, n) out[i] = fp_add(a[i], b[i]);
 }
+__global__ void k_expand_zero(uint32_t* out, const uint32_t* in, size_t n_out, int bits) {
+  GRID_STRIDE(w, n_out) out[w] = (w & ((size_t(1) << bits) - 1)) == 0 ? in[w >> bits] : 0u;
+}
+__global__ void k_mul_factor(uint32_t* io, uint32_t factor, size_t n) { GRID_STRIDE(i, n) io[i] = fp_mul(io[i], factor); }
 __global__ void k_copy(uint32_t* out, const uint32_t* in, size_t n) { GRID_STRIDE(i, n) out[i] = in[i]; }
 __global__ void k_copy4(uint4* out, const uint4* in, size_t n4) { GRID_STRIDE(i, n4) out[i] = in[i]; }
 __global__ void k_zeroize(uint32_t* io, size_t n) {
@@ -457,15 +461,21 @@ struct Scratch {
   void* d = nullptr;
   Scratch(Ctx* c_, const void* host, size_t bytes) : c(c_) {
     R0_CUDA(cudaMallocAsync(&d, bytes ? bytes : 16, c->stream));
-    if (bytes) R0_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (bytes) {
+      // The caller's buffer may be pinned (the header recommends pinned memory for witnesses), and a copy from pinned
+      // memory is truly asynchronous: the caller could free or overwrite it before the GPU reads it. Stage through a
+      // library-owned pageable copy instead - cudaMemcpyAsync from pageable memory returns only after the bytes
+      // have been taken, so `stage` can be released right away. These arguments are small (indices, combo ids, mix).
+      std::vector<unsigned char> stage((const unsigned char*)host, (const unsigned char*)host + bytes);
+      R0_CUDA(cudaMemcpyAsync(d, stage.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    }
   }
   Scratch(Ctx* c_, size_t bytes) : c(c_) { R0_CUDA(cudaMallocAsync(&d, bytes ? bytes : 16, c->stream)); }
   ~Scratch() { cudaFreeAsync(d, c->stream); }
   template <typename T>
   T* as() { return (T*)d; }
 };
-// NOTE: cudaMemcpyAsync from pageable host memory returns after the data has been staged, so the host vectors
-// passed to Scratch may be freed as soon as the constructor returns.
+// Host arguments passed to Scratch may be freed or modified as soon as the constructor returns (see above).
 
 void r0_fri_fold(Ctx* c, uint32_t* out, const uint32_t* in, size_t count, const FpExt& mix) {
   PhaseScope ph(c, "fri_fold", 272.0 * (double)count);
@@ -552,6 +562,22 @@ void r0_scatter(Ctx* c, uint32_t* into, const uint32_t* index_host, size_t index
   LAUNCH_1D(k_scatter, index_len - 1, into, d_index.as<uint32_t>(), index_len - 1, d_off.as<uint32_t>(),
             d_val.as<uint32_t>());
 }
+// device-argument forms (the reference's FFI passes device buffers: risc0_zkp_cuda_scatter, .._eltwise_copy_fp_region)
+void r0_scatter_dev(Ctx* c, uint32_t* into, const uint32_t* index_dev, size_t count, const uint32_t* offsets_dev,
+                    const uint32_t* values_dev) {
+  if (count == 0) return;
+  LAUNCH_1D(k_scatter, count, into, index_dev, count, offsets_dev, values_dev);
+}
+void r0_copy_region_dev(Ctx* c, uint32_t* into, const uint32_t* from_dev, size_t from_rows, size_t from_cols,
+                        size_t from_offset, size_t from_stride, size_t into_offset, size_t into_stride) {
+  if (from_rows == 0 || from_cols == 0) return;
+  LAUNCH_1D(k_copy_region, from_rows * from_cols, into, from_dev + from_offset, from_rows, from_cols, from_stride,
+            into_offset, into_stride);
+}
+void r0_expand_zero_interleave(Ctx* c, uint32_t* out, const uint32_t* in, size_t n_in, int bits) {
+  LAUNCH_1D(k_expand_zero, n_in << bits, out, in, n_in << bits, bits);
+}
+void r0_eltwise_mul_factor(Ctx* c, uint32_t* io, uint32_t factor, size_t n) { LAUNCH_1D(k_mul_factor, n, io, factor, n); }
 void r0_copy_elem_slice(Ctx* c, uint32_t* into, const uint32_t* from_host, size_t from_rows, size_t from_cols,
                         size_t from_offset, size_t from_stride, size_t into_offset, size_t into_stride) {
   if (from_rows == 0 || from_cols == 0) return;

@@ -168,6 +168,18 @@ __global__ void __launch_bounds__(256) p2_hash_fold_kernel(uint32_t* io, size_t 
   o[1] = make_uint4(c[4], c[5], c[6], c[7]);
 }
 
+// generic pair hash with independent pointers (sppark_poseidon2_fold's signature): out[i] = H(in[2i] || in[2i+1])
+__global__ void __launch_bounds__(256) p2_fold_pairs_kernel(uint32_t* out, const uint32_t* in, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c[24];
+  load_pair(c, in + 16 * i);
+  p2_permute(c);
+  uint4* o = reinterpret_cast<uint4*>(out + i * 8);
+  o[0] = make_uint4(c[0], c[1], c[2], c[3]);
+  o[1] = make_uint4(c[4], c[5], c[6], c[7]);
+}
+
 // Several levels per launch. A block takes 2*B consecutive nodes of the level of `in_size` nodes (B = blockDim.x),
 // and produces `levels` levels (B, B/2, ... nodes), each written to its heap position nodes[size + index].
 __global__ void __launch_bounds__(256) p2_fold_tree_kernel(uint32_t* nodes, size_t in_size, int levels) {
@@ -242,6 +254,14 @@ void r0_p2_hash_fold(Ctx* c, uint32_t* io, size_t in_size, size_t out_size) {
   R0_CHECK(in_size == 2 * out_size, "hash_fold: input_size must be 2 * output_size");
   if (out_size == 0) return;
   p2_hash_fold_kernel<<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(io, in_size, out_size);
+  count_launch(c);
+  R0_CUDA(cudaGetLastError());
+}
+
+void r0_p2_fold_pairs(Ctx* c, uint32_t* out, const uint32_t* in, size_t n) {
+  PhaseScope ph(c, "hash_fold", 96.0 * (double)n);
+  if (n == 0) return;
+  p2_fold_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(out, in, n);
   count_launch(c);
   R0_CUDA(cudaGetLastError());
 }

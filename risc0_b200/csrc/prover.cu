@@ -14,6 +14,7 @@
 // call; all 350 query openings are gathered by two launches after the 50 positions have been drawn (drawing them has
 // no side effects on the transcript other than the RNG itself, so the seal is unchanged).
 #include <algorithm>
+#include <memory>
 #include <stdexcept>
 #include <vector>
 
@@ -192,6 +193,7 @@ struct MerkleTree {
   }
   // writes nodes[top_size .. 2*top_size) to the proof and commits the root (merkle.rs:83-96)
   void commit(Ctx* c, Transcript& iop, std::vector<Digest>* roots) {
+    NvtxRange range("commit");   // merkle.rs:85
     std::vector<uint32_t> top(8 * top_size);
     {
       // fetch nodes [1, 2*top_size) in one copy: node 1 is the root, the last top_size of them are the top layer
@@ -250,7 +252,23 @@ class SegmentProver {
       : c_(c), desc_(desc), hash_(hash), po2_(po2), cycles_(size_t(1) << po2), iop_(hash), suite_{hash}, taps_(make_taps(desc)) {
     groups_.resize(taps_.num_groups());
   }
+  // Error paths: pending H2D chunks may still be reading the caller's host buffers and writing the coefficient
+  // buffers that are about to be freed on the compute stream, so drain the copy stream first.
+  ~SegmentProver() {
+    bool pending = false;
+    for (auto& v : uploads_) {
+      for (cudaEvent_t ev : v) {
+        pending = true;
+        cudaEventDestroy(ev);
+      }
+      v.clear();
+    }
+    if (pending) cudaStreamSynchronize(c_->copy_stream);
+  }
+  SegmentProver(const SegmentProver&) = delete;
+  SegmentProver& operator=(const SegmentProver&) = delete;
   Transcript& iop() { return iop_; }
+  bool has_group(size_t g) const { return groups_[g].coeffs.p != nullptr; }
   std::vector<Digest> roots;
   std::vector<uint32_t> query_pos;
 
@@ -299,8 +317,10 @@ class SegmentProver {
 
   // Prover::commit_group (prover.rs:81-108). `witness` is a device pointer, or NULL when prefetch_group() was used.
   void commit_group(size_t g, const uint32_t* witness_dev) {
+    NvtxRange range("commit_group");   // prover.rs:82
     const size_t count = taps_.group_sizes[g];
     PolyGroup& pg = groups_[g];
+    std::unique_ptr<NvtxRange> coeffs_range(new NvtxRange("make_coeffs"));   // prover.rs:39
     if (witness_dev) {
       pg.count = count;
       pg.coeffs = DevBuf(c_, count * cycles_);
@@ -317,19 +337,24 @@ class SegmentProver {
       }
       uploads_[g].clear();
     }
+    coeffs_range.reset();
     finish_group(pg);
     pg.merkle.commit(c_, iop_, &roots);
   }
 
   // Prover::finalize (prover.rs:111-393); globals: mix (36 words) and out (90 words), host Montgomery words
   void finalize(const uint32_t* mix_host, const uint32_t* out_host) {
+    NvtxRange range("finalize");   // prover.rs:115
     const size_t domain = cycles_ * INV_RATE;
     const FpExt poly_mix = iop_.random_ext();
     PolyGroup check;
     check.count = CHECK_SIZE;
     check.coeffs = DevBuf(c_, EXT * domain);
+    {
+      NvtxRange r2("eval_check");   // rv32im/src/prove/hal/cuda.rs:180
     desc_.eval_check(c_, check.coeffs.p, groups_[0].evaluated.p, groups_[1].evaluated.p, groups_[2].evaluated.p, out_host,
                      mix_host, poly_mix, (uint32_t)po2_);
+    }
     r0_ntt_interpolate(c_, check.coeffs.p, EXT, (int)(po2_ + 2), /*zk=*/false, 0);
     finish_group(check);
     check.merkle.commit(c_, iop_, &roots);
@@ -347,6 +372,7 @@ class SegmentProver {
     const FpExt z_pow = ext_pow(z, EXT);
     for (size_t i = 0; i < CHECK_SIZE; i++) which[ntaps + i] = (uint32_t)i;
     {
+      NvtxRange r2("eval_u");   // prover.rs:208
       std::vector<FpExt> xs(all_xs);
       xs.resize(ntaps + CHECK_SIZE, z_pow);
       DevBuf d_which(c_, which.size()), d_xs(c_, xs.size() * 4), d_out(c_, xs.size() * 4);
@@ -364,7 +390,10 @@ class SegmentProver {
     // coeff_u: per-register interpolation, then the 16 check evaluations verbatim (prover.rs:213-246)
     std::vector<FpExt> coeff_u(ntaps + CHECK_SIZE);
     const std::vector<size_t> regs = taps_.regs(0, ntaps);
-    for (size_t r : regs) poly_interpolate(&coeff_u[r], &all_xs[r], &eval_u[r], taps_.taps[r].skip);
+    {
+      NvtxRange r2("poly_interpolate");   // prover.rs:233
+      for (size_t r : regs) poly_interpolate(&coeff_u[r], &all_xs[r], &eval_u[r], taps_.taps[r].skip);
+    }
     for (size_t i = 0; i < CHECK_SIZE; i++) coeff_u[ntaps + i] = eval_u[ntaps + i];
     iop_.write((const uint32_t*)coeff_u.data(), coeff_u.size() * 4);
     iop_.commit(suite_.hash_words((const uint32_t*)coeff_u.data(), coeff_u.size() * 4));
@@ -375,6 +404,7 @@ class SegmentProver {
     DevBuf combos(c_, EXT * cycles_ * (combo_count + 1));
     r0_fill(c_, combos.p, 0, combos.words);
     FpExt cur_mix = ext_one();
+    std::unique_ptr<NvtxRange> mix_range(new NvtxRange("mix_poly_coeffs"));   // prover.rs:284
     for (size_t g = 0; g < groups_.size(); g++) {
       const size_t gsize = taps_.group_sizes[g];
       std::vector<uint32_t> ids;
@@ -387,7 +417,9 @@ class SegmentProver {
       std::vector<uint32_t> ids(CHECK_SIZE, (uint32_t)combo_count);
       r0_mix_poly_coeffs(c_, combos.p, cur_mix, mix, check.coeffs.p, ids.data(), CHECK_SIZE, cycles_);
     }
+    mix_range.reset();
     {
+      NvtxRange r2("load_combos");   // prover.rs:321 (prepare :325, divide :337)
       std::vector<uint32_t> reg_sizes, reg_ids;
       for (size_t r : regs) {
         reg_sizes.push_back(taps_.taps[r].skip);
@@ -413,15 +445,18 @@ class SegmentProver {
       }
     }
     DevBuf final_coeffs(c_, EXT * cycles_);
+    std::unique_ptr<NvtxRange> sum_range(new NvtxRange("sum"));   // prover.rs:358
     r0_eltwise_sum_ext(c_, final_coeffs.p, combos.p, cycles_, combo_count + 1);
     combos.release();
     r0_bit_reverse(c_, final_coeffs.p, EXT, (int)po2_);
+    sum_range.reset();
     fri_prove(std::move(final_coeffs), check);
   }
 
  private:
   // PolyGroup::new (poly_group.rs:63-83): LDE, coefficient bit reversal, Merkle tree over the evaluations
   void finish_group(PolyGroup& pg) {
+    NvtxRange range("poly_group");   // poly_group.rs:70
     const size_t domain = cycles_ * INV_RATE;
     pg.evaluated = DevBuf(c_, pg.count * domain);
     r0_ntt_expand_evaluate(c_, pg.evaluated.p, pg.coeffs.p, pg.count, (int)(po2_ + 2), 2, 0);
@@ -436,6 +471,7 @@ class SegmentProver {
   };
 
   void fri_prove(DevBuf&& in_coeffs, const PolyGroup& check) {  // fri.rs:77-126
+    NvtxRange range("fri_prove");   // fri.rs:94
     const size_t orig_domain = in_coeffs.words / EXT * INV_RATE;
     std::vector<std::unique_ptr<FriRound>> rounds;
     DevBuf first = std::move(in_coeffs);
@@ -507,18 +543,34 @@ class SegmentProver {
 
 using namespace r0;
 
-static void prove_segment(r0b200_ctx* ctx, const CircuitDesc& desc, int hash, uint32_t po2, const uint32_t* code,
-                          const uint32_t* data, const uint32_t* accum, int witness_on_host, r0b200_witness* uploaded,
-                          const uint32_t* global_host,
-                          uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
-                          size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host) {
+// One proof in flight: prove_core split where the protocol splits it. begin() runs everything up to and including the
+// draw of the accum mix (rv32im/src/prove/hal/mod.rs:181-213: version word, info and header commits, code and data
+// groups, MIX_SIZE random elements); the caller computes accum FROM that mix (witgen.accum(.., &mix), :213-216) and
+// finish() commits it and runs Prover::finalize (:217-222). The transcript lives in the handle between the two.
+struct r0b200_proof {
+  r0b200_ctx* ctx;
+  const CircuitDesc& desc;
+  uint32_t po2;
+  SegmentProver prover;
+  std::vector<uint32_t> header, mix;
+  bool on_host = false, uploaded = false;
+  r0b200_proof(r0b200_ctx* c, const CircuitDesc& d, int hash, uint32_t po2_)
+      : ctx(c), desc(d), po2(po2_), prover(c, d, hash, po2_) {}
+};
+
+static r0b200_proof* proof_begin(r0b200_ctx* ctx, const CircuitDesc& desc, int hash, uint32_t po2, const uint32_t* code,
+                                 const uint32_t* data, int witness_on_host, r0b200_witness* uploaded,
+                                 const uint32_t* global_host) {
   R0_CHECK(ctx != nullptr, "null r0b200 context");
   R0_CUDA(cudaSetDevice(ctx->device));
   R0_CHECK(hash == R0B200_HASH_POSEIDON2 || hash == R0B200_HASH_SHA256, "prove: unknown hash suite");
   R0_CHECK(po2 >= 9 && po2 + 2 <= (uint32_t)MAX_LG, "prove: po2 out of range (9..22)");
-  SegmentProver prover(ctx, desc, hash, po2);
+  R0_CHECK(global_host != nullptr, "prove: null globals");
+  std::unique_ptr<r0b200_proof> p(new r0b200_proof(ctx, desc, hash, po2));
+  SegmentProver& prover = p->prover;
   Transcript& iop = prover.iop();
   HostSuite suite{hash};
+  NvtxRange range("prove_begin");
   if (desc.has_version) iop.write(&desc.version, 1);
   auto commit_info = [&](const char* s) {
     uint32_t e[16];
@@ -529,30 +581,47 @@ static void prove_segment(r0b200_ctx* ctx, const CircuitDesc& desc, int hash, ui
   commit_info(desc.info);
   // header: globals (INVALID -> 0) followed by the raw po2 word (rv32im/src/prove/hal/mod.rs:196-206,
   // recursion/src/prove/mod.rs:193-206)
-  std::vector<uint32_t> header(desc.output_size + 1);
+  std::vector<uint32_t>& header = p->header;
+  header.resize(desc.output_size + 1);
   for (size_t i = 0; i < desc.output_size; i++) header[i] = global_host[i] == FP_INVALID ? 0u : global_host[i];
   header[desc.output_size] = po2;
   iop.commit(suite.hash_words(header.data(), header.size()));
   iop.write(header.data(), header.size());
-  const bool on_host = witness_on_host != 0 || uploaded != nullptr;
+  p->on_host = witness_on_host != 0 || uploaded != nullptr;
+  p->uploaded = uploaded != nullptr;
   if (uploaded) {
     R0_CHECK(uploaded->c == ctx && uploaded->po2 == po2, "uploaded witness belongs to another context or size");
     prover.adopt_group(1, uploaded);
     prover.adopt_group(2, uploaded);
-    prover.adopt_group(0, uploaded);
-  } else if (on_host) {
+    if (uploaded->coeffs[0]) prover.adopt_group(0, uploaded);   // legacy: accum uploaded before the mix was known
+  } else if (p->on_host) {
     // uploads are enqueued up front in consumption order; each group's compute waits only for its own chunks
     prover.prefetch_group(1, code);
     prover.prefetch_group(2, data);
-    prover.prefetch_group(0, accum);
   }
-  prover.commit_group(1, on_host ? nullptr : code);
-  prover.commit_group(2, on_host ? nullptr : data);
-  std::vector<uint32_t> mix(desc.mix_size);
-  for (size_t i = 0; i < desc.mix_size; i++) mix[i] = iop.random_elem();
-  prover.commit_group(0, on_host ? nullptr : accum);
-  prover.finalize(mix.data(), header.data());
-  R0_CUDA(cudaStreamSynchronize(ctx->stream));
+  prover.commit_group(1, p->on_host ? nullptr : code);
+  prover.commit_group(2, p->on_host ? nullptr : data);
+  p->mix.resize(desc.mix_size);
+  for (size_t i = 0; i < desc.mix_size; i++) p->mix[i] = iop.random_elem();
+  return p.release();
+}
+
+static void proof_finish(r0b200_proof* p, const uint32_t* accum, int accum_on_host, uint32_t* seal_out_host,
+                         size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
+                         uint32_t* query_pos_out_host) {
+  R0_CUDA(cudaSetDevice(p->ctx->device));
+  SegmentProver& prover = p->prover;
+  Transcript& iop = prover.iop();
+  NvtxRange range("prove_finish");
+  if (prover.has_group(0)) {
+    prover.commit_group(0, nullptr);   // accum came with r0b200_witness_upload
+  } else {
+    R0_CHECK(accum != nullptr, "prove_finish: null accum");
+    if (accum_on_host) prover.prefetch_group(0, accum);
+    prover.commit_group(0, accum_on_host ? nullptr : accum);
+  }
+  prover.finalize(p->mix.data(), p->header.data());
+  R0_CUDA(cudaStreamSynchronize(p->ctx->stream));
   if (seal_len) *seal_len = iop.proof.size();
   R0_CHECK(seal_out_host != nullptr && iop.proof.size() <= seal_cap, "prove: seal buffer too small");
   memcpy(seal_out_host, iop.proof.data(), iop.proof.size() * 4);
@@ -562,6 +631,57 @@ static void prove_segment(r0b200_ctx* ctx, const CircuitDesc& desc, int hash, ui
     memcpy(roots_out_host, prover.roots.data(), prover.roots.size() * 32);
   }
   if (query_pos_out_host) memcpy(query_pos_out_host, prover.query_pos.data(), prover.query_pos.size() * 4);
+}
+
+static void prove_segment(r0b200_ctx* ctx, const CircuitDesc& desc, int hash, uint32_t po2, const uint32_t* code,
+                          const uint32_t* data, const uint32_t* accum, int witness_on_host, r0b200_witness* uploaded,
+                          const uint32_t* global_host,
+                          uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
+                          size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host) {
+  std::unique_ptr<r0b200_proof> p(proof_begin(ctx, desc, hash, po2, code, data, witness_on_host, uploaded, global_host));
+  proof_finish(p.get(), accum, witness_on_host, seal_out_host, seal_cap, seal_len, roots_out_host, roots_cap, nroots,
+               query_pos_out_host);
+}
+
+static const CircuitDesc& circuit_desc(int circuit) {
+  R0_CHECK(circuit == R0B200_CIRCUIT_RV32IM || circuit == R0B200_CIRCUIT_RECURSION, "unknown circuit");
+  return circuit == R0B200_CIRCUIT_RV32IM ? kRv32im : kRecursion;
+}
+
+extern "C" r0b200_err r0b200_prove_begin(r0b200_ctx* ctx, int circuit, int hash, uint32_t po2, const uint32_t* code,
+                                         const uint32_t* data, int witness_on_host, r0b200_witness* uploaded,
+                                         const uint32_t* global_host, uint32_t* mix_out_host, size_t mix_cap,
+                                         r0b200_proof** out) {
+  R0_API_BEGIN
+  R0_CHECK(out != nullptr && mix_out_host != nullptr, "prove_begin: null output");
+  const CircuitDesc& desc = circuit_desc(circuit);
+  R0_CHECK(mix_cap >= desc.mix_size, "prove_begin: mix buffer too small");
+  if (uploaded) {
+    R0_CHECK(uploaded->circuit == circuit, "prove_begin: uploaded witness is for another circuit");
+    po2 = uploaded->po2;
+  }
+  r0b200_proof* p = proof_begin(ctx, desc, hash, po2, code, data, witness_on_host, uploaded, global_host);
+  memcpy(mix_out_host, p->mix.data(), desc.mix_size * 4);
+  *out = p;
+  R0_API_END
+}
+
+extern "C" r0b200_err r0b200_prove_finish(r0b200_proof* proof, const uint32_t* accum, int accum_on_host,
+                                          uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len,
+                                          uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
+                                          uint32_t* query_pos_out_host) {
+  R0_API_BEGIN
+  R0_CHECK(proof != nullptr, "prove_finish: null proof");
+  std::unique_ptr<r0b200_proof> p(proof);   // the handle is consumed, also on failure
+  proof_finish(p.get(), accum, accum_on_host, seal_out_host, seal_cap, seal_len, roots_out_host, roots_cap, nroots,
+               query_pos_out_host);
+  R0_API_END
+}
+
+extern "C" void r0b200_prove_abort(r0b200_proof* proof) {
+  if (!proof) return;
+  cudaSetDevice(proof->ctx->device);
+  delete proof;
 }
 
 extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* code,
@@ -604,8 +724,10 @@ extern "C" r0b200_err r0b200_witness_upload(r0b200_ctx* ctx, int circuit, uint32
   size_t chunk = (size_t(64) << 20) / (cycles * 4);
   if (chunk == 0) chunk = 1;
   const int order[3] = {1, 2, 0};                                // consumption order: code, data, accum
+  R0_CHECK(code_host != nullptr && data_host != nullptr, "witness_upload: null code / data");
   for (int oi = 0; oi < 3; oi++) {
     const int g = order[oi];
+    if (!src[g]) continue;   // accum is normally not known yet (it depends on the mix drawn by prove_begin)
     const size_t count = desc.group_sizes[g];
     w->words[g] = count * cycles;
     R0_CUDA(cudaMallocAsync(&w->coeffs[g], w->words[g] * 4, ctx->copy_stream));

@@ -80,9 +80,30 @@ __global__ void __launch_bounds__(256) sha_fold_kernel(uint32_t* io, size_t in_s
   for (int k = 0; k < 8; k++) io[(out_size + i) * 8 + k] = bswap(st[k]);
 }
 
+// generic pair hash with independent pointers (risc0_zkp_cuda_sha_fold's signature): out[i] = H(in[2i] || in[2i+1])
+__global__ void __launch_bounds__(256) sha_fold_pairs_kernel(uint32_t* out, const uint32_t* in, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t st[8], w[16];
+  sha_init(st);
+#pragma unroll
+  for (int k = 0; k < 16; k++) w[k] = bswap(in[16 * i + k]);
+  sha_compress(st, w);
+#pragma unroll
+  for (int k = 0; k < 8; k++) out[i * 8 + k] = bswap(st[k]);
+}
+
 }  // namespace r0
 
 using namespace r0;
+
+void r0_sha_fold_pairs(Ctx* c, uint32_t* out, const uint32_t* in, size_t n) {
+  PhaseScope ph(c, "hash_fold", 96.0 * (double)n);
+  if (n == 0) return;
+  sha_fold_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(out, in, n);
+  count_launch(c);
+  R0_CUDA(cudaGetLastError());
+}
 
 void r0_sha_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
   PhaseScope ph(c, "hash_rows", 4.0 * (double)rows * (double)cols + 32.0 * (double)rows);

@@ -348,12 +348,65 @@ class SegmentProver:
         hal = self.hal
         n = 1 << po2
         c_code, c_data, c_accum, _ = self.SHAPES[circuit]
-        code, data, accum = _u32(code), _u32(data), _u32(accum)
-        assert code.size == c_code * n and data.size == c_data * n and accum.size == c_accum * n
+        code, data = _u32(code), _u32(data)
+        assert code.size == c_code * n and data.size == c_data * n
+        if accum is not None:
+            accum = _u32(accum)
+            assert accum.size == c_accum * n
         h = C.c_void_p()
         check(hal._l.r0b200_witness_upload(hal._ctx, C.c_int(0 if circuit == "rv32im" else 1), C.c_uint32(po2),
-                                           _np_ptr(code), _np_ptr(data), _np_ptr(accum), C.byref(h)))
+                                           _np_ptr(code), _np_ptr(data), _np_ptr(accum) if accum is not None else None,
+                                           C.byref(h)))
         return (h, (code, data, accum))   # keep the host arrays alive with the handle
+
+    def begin(self, po2, code, data, glob, circuit="rv32im", uploaded=None):
+        """prove_core up to the mix draw (rv32im/src/prove/hal/mod.rs:181-213): commits code and data and returns
+        (proof handle, mix words). The caller computes accum from the mix and calls finish()."""
+        hal = self.hal
+        n = 1 << po2
+        c_code, c_data, _, n_glob = self.SHAPES[circuit]
+        glob = _u32(glob)
+        assert glob.size == n_glob
+        mix = np.zeros(64, dtype=np.uint32)
+        h = C.c_void_p()
+        cid = C.c_int(0 if circuit == "rv32im" else 1)
+        if uploaded is not None:
+            uh, _keep = uploaded
+            try:
+                check(hal._l.r0b200_prove_begin(hal._ctx, cid, hal.hash, C.c_uint32(po2), None, None, C.c_int(1), uh,
+                                                _np_ptr(glob), _np_ptr(mix), C.c_size_t(mix.size), C.byref(h)))
+            finally:
+                hal._l.r0b200_witness_free(uh)
+        else:
+            on_host = isinstance(data, np.ndarray)
+            if on_host:
+                code, data = _u32(code), _u32(data)
+                assert code.size == c_code * n and data.size == c_data * n
+                ptrs = [_np_ptr(code), _np_ptr(data)]
+            else:
+                assert code.size() == c_code * n and data.size() == c_data * n
+                ptrs = [code.ptr, data.ptr]
+            check(hal._l.r0b200_prove_begin(hal._ctx, cid, hal.hash, C.c_uint32(po2), ptrs[0], ptrs[1],
+                                            C.c_int(1 if on_host else 0), None, _np_ptr(glob), _np_ptr(mix),
+                                            C.c_size_t(mix.size), C.byref(h)))
+        nmix = 36 if circuit == "rv32im" else 20
+        return h, mix[:nmix].copy()
+
+    def finish(self, proof, accum):
+        """commit accum, eval_check, DEEP, FRI -> (seal, roots, query positions); consumes the handle"""
+        hal = self.hal
+        on_host = isinstance(accum, np.ndarray)
+        if on_host:
+            accum = _u32(accum)
+        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
+        check(hal._l.r0b200_prove_finish(proof, _np_ptr(accum) if on_host else accum.ptr, C.c_int(1 if on_host else 0),
+                                         _np_ptr(self._seal), C.c_size_t(self.seal_cap), C.byref(seal_len),
+                                         _np_ptr(self._roots), C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
+        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
+                self._qpos.copy())
+
+    def abort(self, proof):
+        self.hal._l.r0b200_prove_abort(proof)
 
     def prove_uploaded(self, uploaded, glob):
         hal = self.hal

@@ -299,6 +299,26 @@ def poly_divide_unchecked(poly, z):
     return poly, ok
 
 
+def poly_divide(poly, z):
+    """core/poly.rs:81-89: returns (quotient in place of the input, remainder)"""
+    poly = u32(poly).copy()
+    rem = np.zeros(4, dtype=np.uint32)
+    lib().orc_poly_divide(ptr(poly), _u64(len(poly) // 4), ptr(u32(z)), ptr(rem))
+    return poly, rem
+
+
+def rv32im_poly_mix_pows(poly_mix):
+    out = np.zeros(4 * 458, dtype=np.uint32)
+    lib().orc_rv32im_poly_mix_pows.restype = C.c_uint32
+    n = lib().orc_rv32im_poly_mix_pows(ptr(u32(poly_mix)), ptr(out))
+    return out[:4 * n].copy()
+
+
+def rou_fwd(k):
+    lib().orc_rou_fwd.restype = C.c_uint32
+    return int(lib().orc_rou_fwd(C.c_uint32(k)))
+
+
 def rv32im_eval_check(accum, data, mix, out, poly_mix, po2, begin=0, end=None):
     load_ref()
     domain = 4 << po2
@@ -321,6 +341,15 @@ def prove_rv32im(po2, code, data, accum, glob, kind=POSEIDON2):
                                   ptr(u32(glob)), ptr(seal), _u64(cap), C.byref(n), ptr(roots), _u64(16), C.byref(nr),
                                   ptr(qpos)))
     return seal[:n.value].copy(), roots[:8 * nr.value].reshape(-1, 8).copy(), qpos
+
+
+def prove_rv32im_mix(po2, code, data, glob, kind=POSEIDON2):
+    """the accum mix (36 words) the transcript yields after the code and data commits
+    (rv32im/src/prove/hal/mod.rs:209-213)"""
+    mix = np.zeros(36, dtype=np.uint32)
+    _check(lib().orc_prove_rv32im_mix(C.c_int(kind), C.c_uint32(po2), ptr(u32(code)), ptr(u32(data)), ptr(u32(glob)),
+                                      ptr(mix)))
+    return mix
 
 
 def prove_hello(po2, accum, code, data, kind=POSEIDON2):

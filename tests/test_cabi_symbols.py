@@ -14,6 +14,24 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
 
 
+def test_library_exports_the_reference_symbol_table():
+    """include/r0b200_compat.h: the names risc0/sys/src/cuda.rs:19-80, risc0/sys/kernels/zkp/cuda/ffi.cu:25-145 and
+    the circuit -sys crates declare, so the unmodified hal/cuda.rs can link against libr0b200.so"""
+    names = _lib.compat_symbols()
+    want = {"risc0_zkp_cuda_eltwise_add_fp", "risc0_zkp_cuda_eltwise_mul_factor_fp", "risc0_zkp_cuda_eltwise_copy_fp",
+            "risc0_zkp_cuda_eltwise_copy_fp_region", "risc0_zkp_cuda_eltwise_sum_fpext", "risc0_zkp_cuda_eltwise_zeroize_fp",
+            "risc0_zkp_cuda_eltwise_zeroize_fpext", "risc0_zkp_cuda_fri_fold", "risc0_zkp_cuda_mix_poly_coeffs",
+            "risc0_zkp_cuda_batch_bit_reverse", "risc0_zkp_cuda_batch_evaluate_any", "risc0_zkp_cuda_gather_sample",
+            "risc0_zkp_cuda_scatter", "risc0_zkp_cuda_sha_rows", "risc0_zkp_cuda_sha_fold", "risc0_zkp_cuda_combos_prepare",
+            "sppark_init", "sppark_batch_expand", "sppark_batch_NTT", "sppark_batch_iNTT", "sppark_batch_zk_shift",
+            "sppark_poseidon2_fold", "sppark_poseidon2_rows", "sppark_poseidon254_fold", "sppark_poseidon254_rows",
+            "supra_poly_divide", "risc0_circuit_rv32im_cuda_eval_check", "risc0_circuit_recursion_cuda_eval_check"}
+    assert want <= set(names), want - set(names)
+    lib = _lib.load_library()
+    for n in names:
+        assert hasattr(lib, n), n
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

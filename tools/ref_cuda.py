@@ -14,10 +14,18 @@ def available():
     return os.path.exists(LIB)
 
 
-def lib():
+def use(path):
+    """bind the harness to another library exporting the same symbol table (libr0b200.so's compat layer, so that
+    the same calls can be run against the reference's kernels and against ours)"""
+    global _lib
+    _lib = None
+    lib(path)
+
+
+def lib(path=None):
     global _lib
     if _lib is None:
-        _lib = C.CDLL(LIB)
+        _lib = C.CDLL(path or LIB)
         for n in ("risc0_zkp_cuda_batch_bit_reverse", "risc0_zkp_cuda_fri_fold", "risc0_zkp_cuda_mix_poly_coeffs",
                   "risc0_zkp_cuda_batch_evaluate_any", "risc0_zkp_cuda_eltwise_sum_fpext", "risc0_zkp_cuda_eltwise_copy_fp",
                   "risc0_zkp_cuda_sha_rows", "risc0_zkp_cuda_sha_fold", "risc0_zkp_cuda_gather_sample",
