@@ -96,6 +96,49 @@ extern "C" const char* orc_rv32im_eval_check(uint32_t* check, const uint32_t* ac
   ORC_CATCH
 }
 
+// Constraint check of a RAW (un-extended) rv32im witness: is every constraint zero on every row? The generated poly_fp
+// reads a tap at row (cycle - INV_RATE * back) mod steps (rust_poly_fp_0.cpp:22,114), so the N trace rows are placed at
+// every INV_RATE-th row of a steps = INV_RATE * N matrix and poly_fp is evaluated at those rows only. This is what "the
+// witness satisfies the circuit" means; the prover itself never checks it. bad_rows = rows with a non-zero result.
+extern "C" const char* orc_rv32im_check_constraints(const uint32_t* accum, const uint32_t* data, const uint32_t* mix,
+                                                    const uint32_t* out, const uint32_t* poly_mix, uint32_t po2,
+                                                    uint64_t* bad_rows, uint64_t* first_bad) {
+  ORC_TRY
+  if (!g_rv32im_poly_fp) throw std::runtime_error("oracle/_ref poly_fp not loaded (call orc_load_ref)");
+  const size_t N = size_t(1) << po2, steps = N * INV_RATE;
+  FpExt pm(Fp::raw(poly_mix[0]), Fp::raw(poly_mix[1]), Fp::raw(poly_mix[2]), Fp::raw(poly_mix[3]));
+  std::vector<FpExt> pows(RV32IM_NUM_POLY_MIX_POWERS);
+  for (size_t i = 0; i < pows.size(); i++) pows[i] = pm.pow(RV32IM_POLY_MIX_POWERS[i]);
+  std::vector<Fp> acc4(103 * steps), dat4(211 * steps);
+  for (size_t c = 0; c < 103; c++)
+    for (size_t r = 0; r < N; r++) acc4[c * steps + INV_RATE * r] = Fp::raw(accum[c * N + r]);
+  for (size_t c = 0; c < 211; c++)
+    for (size_t r = 0; r < N; r++) dat4[c * steps + INV_RATE * r] = Fp::raw(data[c * N + r]);
+  uint64_t bad = 0, first = UINT64_MAX;
+  std::string err;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : bad) reduction(min : first)
+  for (size_t r = 0; r < N; r++) {
+    Fp* args[4] = {acc4.data(), dat4.data(), (Fp*)out, (Fp*)mix};
+    FpExt tot;
+    const char* e = g_rv32im_poly_fp(INV_RATE * r, steps, pows.data(), args, &tot);
+    if (e) {
+#pragma omp critical
+      err = e;
+      continue;
+    }
+    bool zero = true;
+    for (size_t k = 0; k < EXT_SIZE; k++) zero = zero && tot.e[k].v == 0;
+    if (!zero) {
+      bad++;
+      if (r < first) first = r;
+    }
+  }
+  if (!err.empty()) throw std::runtime_error(err);
+  *bad_rows = bad;
+  *first_bad = first;
+  ORC_CATCH
+}
+
 // HelloCircuit constraints (verify/mod.rs:683-704): u0 = 0, u1 = 0, u2*(u2-1) = 0
 static void hello_eval_check(Fp* check, const std::vector<const Fp*>& g, FpExt poly_mix, size_t po2, size_t steps) {
   size_t domain = steps * INV_RATE;

@@ -343,6 +343,15 @@ def prove_rv32im(po2, code, data, accum, glob, kind=POSEIDON2):
     return seal[:n.value].copy(), roots[:8 * nr.value].reshape(-1, 8).copy(), qpos
 
 
+def rv32im_check_constraints(accum, data, mix, out, poly_mix, po2):
+    """(number of trace rows on which the rv32im constraint polynomial is non-zero, first such row or None)"""
+    load_ref()
+    bad, first = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().orc_rv32im_check_constraints(ptr(u32(accum)), ptr(u32(data)), ptr(u32(mix)), ptr(u32(out)),
+                                              ptr(u32(poly_mix)), C.c_uint32(po2), C.byref(bad), C.byref(first)))
+    return bad.value, (first.value if bad.value else None)
+
+
 def prove_rv32im_mix(po2, code, data, glob, kind=POSEIDON2):
     """the accum mix (36 words) the transcript yields after the code and data commits
     (rv32im/src/prove/hal/mod.rs:209-213)"""

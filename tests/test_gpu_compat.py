@@ -38,6 +38,13 @@ def L():
     return lib
 
 
+def dev(hal, kind, name, host):
+    """upload through `hal` and wait: the compat entry points run on the library's default context (another stream)"""
+    buf = getattr(hal, "copy_from_" + kind)(name, host)
+    hal.sync()
+    return buf
+
+
 def ok(e):
     if isinstance(e, SpparkError):
         assert e.code == 0, e.message
@@ -53,19 +60,19 @@ def test_ref_harness_against_compat_layer(hal):
         rng = np.random.default_rng(7)
         lg, cols = 13, 5
         vals = O.rand_elems(rng, cols << lg)
-        b = hal.copy_from_elem("b", vals)
+        b = dev(hal, "elem", "b", vals)
         R.batch_bit_reverse(b, lg, cols << lg)
         assert np.array_equal(b.view(), O.batch_bit_reverse(vals, cols))
         count = 1 << 9
         inp_h = O.rand_elems(rng, 64 * count)
         mix = O.rand_ext(rng)
         o = hal.alloc_elem("o", 4 * count)
-        R.fri_fold(o, hal.copy_from_elem("in", inp_h), hal.copy_from_extelem("mix", mix), count)
+        R.fri_fold(o, dev(hal, "elem", "in", inp_h), dev(hal, "extelem", "mix", mix), count)
         assert np.array_equal(o.view(), O.fri_fold(inp_h, mix))
         to_add = 5
         src_h = O.rand_elems(rng, 4 * to_add * count)
         s = hal.alloc_elem("s", 4 * count)
-        R.eltwise_sum_fpext(s, hal.copy_from_extelem("src", src_h), to_add, count)
+        R.eltwise_sum_fpext(s, dev(hal, "extelem", "src", src_h), to_add, count)
         assert np.array_equal(s.view(), O.eltwise_sum_extelem(src_h, count))
         # mix_poly_coeffs + batch_evaluate_any
         n, S = 1 << 11, 23
@@ -73,21 +80,21 @@ def test_ref_harness_against_compat_layer(hal):
         combos = rng.integers(0, 4, size=S).astype(np.uint32)
         out0 = O.rand_elems(rng, 4 * 5 * n)
         ms, m = O.rand_ext(rng), O.rand_ext(rng)
-        d_in = hal.copy_from_elem("in", in_h)
-        d_out = hal.copy_from_extelem("out", out0)
-        R.mix_poly_coeffs(d_out, d_in, hal.copy_from_u32("c", combos), hal.copy_from_extelem("ms", ms),
-                          hal.copy_from_extelem("m", m), S, n)
+        d_in = dev(hal, "elem", "in", in_h)
+        d_out = dev(hal, "extelem", "out", out0)
+        R.mix_poly_coeffs(d_out, d_in, dev(hal, "u32", "c", combos), dev(hal, "extelem", "ms", ms),
+                          dev(hal, "extelem", "m", m), S, n)
         assert np.array_equal(d_out.view(), O.mix_poly_coeffs(out0, ms, m, in_h, combos, S, n))
         E = 17
         which = rng.integers(0, S, size=E).astype(np.uint32)
         xs = O.rand_elems(rng, 4 * E)
         e = hal.alloc_extelem("e", E)
-        R.batch_evaluate_any(e, d_in, hal.copy_from_u32("w", which), hal.copy_from_extelem("xs", xs), E, n)
+        R.batch_evaluate_any(e, d_in, dev(hal, "u32", "w", which), dev(hal, "extelem", "xs", xs), E, n)
         assert np.array_equal(e.view(), O.batch_evaluate_any(in_h, S, which, xs))
         # sha rows / fold / gather
         rows, c = 1 << 9, 19
         m_h = O.rand_elems(rng, rows * c)
-        d_m = hal.copy_from_elem("m", m_h)
+        d_m = dev(hal, "elem", "m", m_h)
         nodes = hal.alloc_digest("n", 2 * rows)
         R.sha_rows(nodes.slice(rows, rows), d_m, rows, c)
         size = rows
@@ -107,7 +114,7 @@ def test_ref_harness_against_compat_layer(hal):
 def test_sppark_ntt_family(hal, L, lg, count):
     rng = np.random.default_rng(100 + lg)
     vals = O.rand_elems(rng, count << lg)
-    io = hal.copy_from_elem("io", vals)
+    io = dev(hal, "elem", "io", vals)
     ok(L.sppark_init())
     ok(L.sppark_batch_iNTT(io.ptr, u32(lg), u32(count)))
     coeffs = O.batch_interpolate_ntt(vals, count)
@@ -129,13 +136,14 @@ def test_sppark_poseidon2(hal, L, rows, cols):
     rng = np.random.default_rng(200 + cols)
     m_h = O.rand_elems(rng, rows * cols)
     out = hal.alloc_digest("d", rows)
-    ok(L.sppark_poseidon2_rows(out.ptr, hal.copy_from_elem("m", m_h).ptr, u32(rows), u32(cols)))
+    d_m = dev(hal, "elem", "m", m_h)
+    ok(L.sppark_poseidon2_rows(out.ptr, d_m.ptr, u32(rows), u32(cols)))
     want = O.hash_rows(O.POSEIDON2, m_h, rows)
     assert np.array_equal(out.view(), want)
     if rows >= 2 and rows & (rows - 1) == 0:
         nodes_h = np.zeros(16 * rows, dtype=np.uint32)
         nodes_h[8 * rows:] = want
-        nodes = hal.copy_from_digest("n", nodes_h)
+        nodes = dev(hal, "digest", "n", nodes_h)
         size = rows
         while size > 1:   # hal/cuda.rs:145-155: output = io + output_size, input = io + 2 * output_size
             ok(L.sppark_poseidon2_fold(C.c_void_p(nodes.alloc.ptr + (size // 2) * 32), C.c_void_p(nodes.alloc.ptr + size * 32),
@@ -151,7 +159,7 @@ def test_supra_poly_divide_and_eltwise(hal, L):
     n = 1 << 12
     poly = O.rand_elems(rng, 4 * n)
     z = O.rand_ext(rng)
-    d = hal.copy_from_extelem("p", poly)
+    d = dev(hal, "extelem", "p", poly)
     rem = np.zeros(4, dtype=np.uint32)
     ok(L.supra_poly_divide(d.ptr, C.c_size_t(n), rem.ctypes.data_as(C.POINTER(u32)), z.ctypes.data_as(C.POINTER(u32))))
     want_q, want_r = O.poly_divide(poly, z)
@@ -161,6 +169,7 @@ def test_supra_poly_divide_and_eltwise(hal, L):
     for count in (1, 9, 1001, 1025):
         a_h, b_h = O.rand_elems(rng, count), O.rand_elems(rng, count)
         a, b, o = hal.copy_from_elem("a", a_h), hal.copy_from_elem("b", b_h), hal.alloc_elem("o", count)
+        hal.sync()
         ok(L.risc0_zkp_cuda_eltwise_add_fp(o.ptr, a.ptr, b.ptr, u32(count)))
         assert np.array_equal(o.view(), O.eltwise_add_elem(a_h, b_h))
         ok(L.risc0_zkp_cuda_eltwise_copy_fp(o.ptr, a.ptr, u32(count)))
@@ -170,7 +179,7 @@ def test_supra_poly_divide_and_eltwise(hal, L):
         assert np.array_equal(O.decode(o.view()), (O.decode(a_h).astype(np.uint64) * 7 % O.P).astype(np.uint32))
         inv = a_h.copy()
         inv[::3] = 0xFFFFFFFF
-        z_ = hal.copy_from_elem("z", inv)
+        z_ = dev(hal, "elem", "z", inv)
         ok(L.risc0_zkp_cuda_eltwise_zeroize_fp(z_.ptr, u32(count)))
         assert np.array_equal(z_.view(), O.eltwise_zeroize_elem(inv))
     # scatter / copy_region with device-side arguments (hal/cuda.rs:850-935)
@@ -180,14 +189,13 @@ def test_supra_poly_divide_and_eltwise(hal, L):
     offsets = rng.permutation(rows * cols)[:2 * rows].astype(np.uint32)
     values = O.rand_elems(rng, 2 * rows)
     into = hal.copy_from_elem("into", into_h)
-    ok(L.risc0_zkp_cuda_scatter(into.ptr, hal.copy_from_u32("i", index).ptr, hal.copy_from_u32("o", offsets).ptr,
-                                hal.copy_from_elem("v", values).ptr, u32(rows)))
+    d_i, d_o, d_v = dev(hal, "u32", "i", index), dev(hal, "u32", "o", offsets), dev(hal, "elem", "v", values)
+    ok(L.risc0_zkp_cuda_scatter(into.ptr, d_i.ptr, d_o.ptr, d_v.ptr, u32(rows)))
     assert np.array_equal(into.view(), O.scatter(into_h, index, offsets, values))
     frm = O.rand_elems(rng, 4 * 10)
     into2_h = O.rand_elems(rng, 200)
-    into2 = hal.copy_from_elem("into2", into2_h)
-    ok(L.risc0_zkp_cuda_eltwise_copy_fp_region(into2.ptr, hal.copy_from_elem("f", frm).ptr, u32(3), u32(7), u32(2), u32(10),
-                                               u32(11), u32(50)))
+    into2, d_f = dev(hal, "elem", "into2", into2_h), dev(hal, "elem", "f", frm)
+    ok(L.risc0_zkp_cuda_eltwise_copy_fp_region(into2.ptr, d_f.ptr, u32(3), u32(7), u32(2), u32(10), u32(11), u32(50)))
     assert np.array_equal(into2.view(), O.eltwise_copy_elem_slice(into2_h, frm, 3, 7, 2, 10, 11, 50))
 
 
@@ -202,9 +210,9 @@ def test_rv32im_eval_check_compat(hal, L):
     rou = np.array([O.rou_fwd(po2 + 2)], dtype=np.uint32)
     check = hal.alloc_elem("check", 4 * dom)
     p = lambda a: a.ctypes.data_as(C.POINTER(u32))
-    ok(L.risc0_circuit_rv32im_cuda_eval_check(check.ptr, hal.copy_from_elem("c", code).ptr, hal.copy_from_elem("d", data).ptr,
-                                              hal.copy_from_elem("a", accum).ptr, hal.copy_from_elem("m", mix).ptr,
-                                              hal.copy_from_elem("o", out).ptr, p(rou), u32(po2), u32(dom), p(pows)))
+    bufs = [dev(hal, "elem", n_, a_) for n_, a_ in (("c", code), ("d", data), ("a", accum), ("m", mix), ("o", out))]
+    ok(L.risc0_circuit_rv32im_cuda_eval_check(check.ptr, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, bufs[4].ptr,
+                                              p(rou), u32(po2), u32(dom), p(pows)))
     want = O.rv32im_eval_check(accum, data, mix, out, poly_mix, po2)
     assert np.array_equal(check.view(), want)
     bad = rou.copy()
