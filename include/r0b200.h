@@ -185,6 +185,54 @@ r0b200_err r0b200_prove_recursion(r0b200_ctx* ctx, int hash, uint32_t po2, const
                                   uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
                                   size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host);
 
+/* ---- witness generation on the device (CircuitWitnessGenerator / CircuitAccumulator) ----
+ * rv32im/src/prove/hal/mod.rs:82-102; replaces risc0_circuit_rv32im_cuda_witgen / _cuda_accum
+ * (rv32im-sys/src/lib.rs:105-119, kernels/cuda/ffi.cu:431-512; CPU spec kernels/cxx/ffi.cpp:265-365).
+ * r0b200_preflight_trace is RawPreflightTrace (rv32im-sys/src/lib.rs:63-72) with HOST pointers: `cycles` = array of
+ * RawPreflightCycle (36 bytes each), `txns` = array of RawMemoryTransaction (20 bytes each). */
+typedef struct {
+  const void* cycles;
+  const void* txns;
+  const uint8_t* bigint_bytes;
+  uint32_t txns_len;
+  uint32_t bigint_bytes_len;
+  uint32_t table_split_cycle;
+} r0b200_preflight_trace;
+typedef struct r0b200_trace r0b200_trace;
+/* Copies a trace of `cycles` (= 2^po2) cycles to the device (stream-ordered; pinned memory makes it asynchronous) and
+ * bucket-sorts the cycles of each phase by (major, minor) there, which is the order the step kernels walk. */
+r0b200_err r0b200_trace_upload(r0b200_ctx* ctx, const r0b200_preflight_trace* trace_host, uint32_t cycles,
+                               r0b200_trace** out);
+void r0b200_trace_free(r0b200_trace* trace);
+/* generate_witness: fills `data` (211 x cycles, device) and the output cells of `global` (90 words, device) for every
+ * cycle. As in WitnessGenerator::new (prove/witgen/mod.rs:144-165) the caller has filled data with INVALID and applied
+ * the injector scatter, and uploaded the global vector. mode: StepMode (0 parallel, 1 forward, 2 reverse) - the step
+ * functions are order-independent inside a phase, so all three run the same sorted parallel schedule. Synchronises and
+ * reports the first failed check ("Inconsistent set", "Read of unset value", eqz, trace mismatch) as the error. */
+r0b200_err r0b200_witgen_rv32im(r0b200_ctx* ctx, uint32_t mode, r0b200_trace* trace, uint32_t* global, uint32_t* data);
+/* step_accum: fills `accum` (103 x cycles, device; INVALID-filled, bigint-accum cells scattered by the caller) from
+ * data, global and mix (36 words, device), then the 4-column prefix sum and the back-propagation of the totals. */
+r0b200_err r0b200_accum_rv32im(r0b200_ctx* ctx, r0b200_trace* trace, uint32_t* data, uint32_t* accum, uint32_t* global,
+                               uint32_t* mix);
+
+/* SegmentProverImpl::prove_core (rv32im/src/prove/hal/mod.rs:143-224) from a PreflightResults
+ * (prove/witgen/mod.rs:55-88), everything on the device: WitnessGenerator::new (INVALID fill, injector scatter,
+ * generate_witness, zeroize), commit code + data, mix draw, WitnessGenerator::accum (step_accum from that mix), commit
+ * accum, finalize -> seal. Host inputs: the trace, the global vector (90 words, INVALID where the witness generator
+ * fills the value) and the injector as the reference builds it (CSR: index[cycles + 1], word offsets col * cycles + row,
+ * Montgomery values; witgen/mod.rs:226-270,320-370). acc_*: the BigIntAccum injector of WitnessGenerator::accum
+ * (:186-207) - NOTE it depends on the mix; pass NULL / 0 for segments without bigint cycles (a segment with bigint
+ * cycles must use prove_begin / accum / prove_finish). global_out_host (90 words, may be NULL) receives the globals
+ * after witness generation (zeroized), i.e. the journal side of the claim. */
+r0b200_err r0b200_prove_segment_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const r0b200_preflight_trace* trace_host,
+                                       const uint32_t* global_host, const uint32_t* inj_index_host, size_t inj_index_len,
+                                       const uint32_t* inj_offsets_host, const uint32_t* inj_values_host,
+                                       const uint32_t* acc_index_host, size_t acc_index_len,
+                                       const uint32_t* acc_offsets_host, const uint32_t* acc_values_host,
+                                       uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
+                                       size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host,
+                                       uint32_t* global_out_host);
+
 /* ---- pipelined host witnesses ----
  * The reference keeps the GPU busy with depth-2 work queues (r0vm/src/actors/worker.rs:70-76,185-204): while segment s is
  * proved, segment s+1 is prepared. r0b200_witness_upload() enqueues the host->device copy of a witness (circuit 0 =

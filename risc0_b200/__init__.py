@@ -5,4 +5,4 @@ host-side mirror of the reference's `risc0_zkp::hal::Hal` trait over that ABI (`
 tests and bench.py. There is NO CPU fallback: without the built library or without a CUDA device the calls raise.
 """
 from ._lib import LIB_PATH, R0B200Error, lib_available, load_library  # noqa: F401
-from .hal import B200Hal, Buffer, SegmentProver  # noqa: F401
+from .hal import B200Hal, Buffer, DeviceTrace, Rv32imCircuitHal, SegmentProver, WitnessGenerator  # noqa: F401

@@ -1,5 +1,6 @@
 // Host-side launcher prototypes (one per kernel family). Internal to libr0b200.so.
 #pragma once
+#include "../../include/r0b200.h"
 #include "ctx.h"
 
 void r0_ntt_init_tables(r0::Ctx* c);
@@ -68,3 +69,10 @@ void r0_eval_check_rv32im(r0::Ctx* c, uint32_t* check, const uint32_t* accum, co
 void r0_eval_check_recursion(r0::Ctx* c, uint32_t* check, const uint32_t* accum, const uint32_t* code,
                              const uint32_t* data, const uint32_t* global_host, const uint32_t* mix_host,
                              const r0::FpExt& poly_mix, uint32_t po2);
+
+// rv32im witness generation / accumulation on the device (witgen.cu)
+r0b200_trace* r0_trace_upload(r0::Ctx* c, const r0b200_preflight_trace* trace_host, uint32_t cycles);
+void r0_trace_free(r0b200_trace* t);
+void r0_witgen_rv32im(r0::Ctx* c, r0b200_trace* t, uint32_t* global, uint32_t* data, bool sync_check);
+void r0_accum_rv32im(r0::Ctx* c, r0b200_trace* t, uint32_t* data, uint32_t* accum, uint32_t* global, uint32_t* mix,
+                     bool sync_check);

@@ -684,6 +684,66 @@ extern "C" void r0b200_prove_abort(r0b200_proof* proof) {
   delete proof;
 }
 
+// prove_core from a PreflightResults (rv32im/src/prove/hal/mod.rs:143-224): WitnessGenerator::new on the device
+// (prove/witgen/mod.rs:130-176: INVALID fill, injector scatter, generate_witness, zeroize), the two group commits, the
+// mix draw, WitnessGenerator::accum (:178-224: step_accum from that mix, zeroize), the accum commit and finalize.
+extern "C" r0b200_err r0b200_prove_segment_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2,
+                                                  const r0b200_preflight_trace* trace_host, const uint32_t* global_host,
+                                                  const uint32_t* inj_index_host, size_t inj_index_len,
+                                                  const uint32_t* inj_offsets_host, const uint32_t* inj_values_host,
+                                                  const uint32_t* acc_index_host, size_t acc_index_len,
+                                                  const uint32_t* acc_offsets_host, const uint32_t* acc_values_host,
+                                                  uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len,
+                                                  uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
+                                                  uint32_t* query_pos_out_host, uint32_t* global_out_host) {
+  R0_API_BEGIN
+  R0_CHECK(ctx != nullptr && trace_host != nullptr && global_host != nullptr, "prove_segment: null argument");
+  R0_CHECK(po2 >= 9 && po2 + 2 <= (uint32_t)MAX_LG, "prove_segment: po2 out of range (9..22)");
+  R0_CUDA(cudaSetDevice(ctx->device));
+  NvtxRange range("prove_core");
+  const size_t cycles = size_t(1) << po2;
+  const CircuitDesc& d = kRv32im;
+  struct TraceGuard {
+    r0b200_trace* t;
+    ~TraceGuard() { r0_trace_free(t); }
+  } trace{nullptr};
+  DevBuf data, code, accum, d_global(ctx, d.output_size), d_mix(ctx, d.mix_size);
+  std::vector<uint32_t> global(d.output_size);
+  {
+    NvtxRange r2("witness_generator_new");
+    trace.t = r0_trace_upload(ctx, trace_host, (uint32_t)cycles);
+    data = DevBuf(ctx, d.group_sizes[2] * cycles);
+    r0_fill(ctx, data.p, FP_INVALID, data.words);
+    if (inj_index_len >= 2) r0_scatter(ctx, data.p, inj_index_host, inj_index_len, inj_offsets_host, inj_values_host);
+    R0_CUDA(cudaMemcpyAsync(d_global.p, global_host, d.output_size * 4, cudaMemcpyHostToDevice, ctx->stream));
+    {
+      NvtxRange r3("witgen");
+      r0_witgen_rv32im(ctx, trace.t, d_global.p, data.p, /*sync_check=*/true);
+    }
+    NvtxRange r4("zeroize");
+    r0_eltwise_zeroize(ctx, d_global.p, d.output_size);
+    r0_eltwise_zeroize(ctx, data.p, data.words);
+    code = DevBuf(ctx, d.group_sizes[1] * cycles);
+    r0_fill(ctx, code.p, 0, code.words);   // code is INVALID-initialised then zeroized: all zero (witgen/mod.rs:149,168)
+    R0_CUDA(cudaMemcpyAsync(global.data(), d_global.p, d.output_size * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    R0_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (global_out_host) memcpy(global_out_host, global.data(), d.output_size * 4);
+  std::unique_ptr<r0b200_proof> p(proof_begin(ctx, d, hash, po2, code.p, data.p, 0, nullptr, global.data()));
+  {
+    NvtxRange r2("accumulate");
+    accum = DevBuf(ctx, d.group_sizes[0] * cycles);
+    r0_fill(ctx, accum.p, FP_INVALID, accum.words);
+    if (acc_index_len >= 2) r0_scatter(ctx, accum.p, acc_index_host, acc_index_len, acc_offsets_host, acc_values_host);
+    R0_CUDA(cudaMemcpyAsync(d_mix.p, p->mix.data(), d.mix_size * 4, cudaMemcpyHostToDevice, ctx->stream));
+    r0_accum_rv32im(ctx, trace.t, data.p, accum.p, d_global.p, d_mix.p, /*sync_check=*/true);
+    r0_eltwise_zeroize(ctx, accum.p, accum.words);
+  }
+  proof_finish(p.get(), accum.p, 0, seal_out_host, seal_cap, seal_len, roots_out_host, roots_cap, nroots,
+               query_pos_out_host);
+  R0_API_END
+}
+
 extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* code,
                                           const uint32_t* data, const uint32_t* accum, int witness_on_host,
                                           const uint32_t* global_host, uint32_t* seal_out_host, size_t seal_cap,

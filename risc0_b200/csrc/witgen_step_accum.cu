@@ -1,0 +1,22 @@
+// One thread per cycle of the sorted order (see witgen.cu): the kernel that instantiates the generated rv32im step
+// function `step_TopAccum` (gen/witgen_rv32im.inc, tools/gen_witgen.py). Own translation unit because ptxas needs minutes for it.
+#include <cuda_runtime.h>
+
+#include "witgen_rt.cuh"
+
+namespace r0wg {
+#include "gen/witgen_rv32im.inc"
+
+__global__ void __launch_bounds__(128) k_step_accum(const WShared* s, const uint32_t* order, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t cycle = order[i];
+  WCtx ctx{s, cycle, s->cycles[cycle].txn_idx};
+  step_TopAccum(ctx, BUF_ACCUM, BUF_DATA, BUF_GLOBAL, BUF_MIX);
+}
+
+void launch_step_accum(cudaStream_t stream, const WShared* s, const uint32_t* order, uint32_t count) {
+  k_step_accum<<<(count + 127) / 128, 128, 0, stream>>>(s, order, count);
+}
+
+}  // namespace r0wg

@@ -326,6 +326,92 @@ class B200Hal:
                                                   out.ptr, _np_ptr(_u32(poly_mix)), C.c_uint32(po2)))
 
 
+class PreflightTraceStruct(C.Structure):
+    """r0b200_preflight_trace = RawPreflightTrace (rv32im-sys/src/lib.rs:63-72) with host pointers"""
+    _fields_ = [("cycles", C.c_void_p), ("txns", C.c_void_p), ("bigint_bytes", C.c_void_p), ("txns_len", C.c_uint32),
+                ("bigint_bytes_len", C.c_uint32), ("table_split_cycle", C.c_uint32)]
+
+
+def _trace_struct(pf):
+    """pf: risc0_b200.preflight.PreflightResults (or anything with .cycles / .txns structured arrays, .bigint_bytes,
+    .table_split_cycle). Returns (struct, keep-alive tuple)."""
+    cycles = np.ascontiguousarray(pf.cycles)
+    txns = np.ascontiguousarray(pf.txns)
+    bigint = np.ascontiguousarray(pf.bigint_bytes, dtype=np.uint8)
+    assert cycles.dtype.itemsize == 36 and txns.dtype.itemsize == 20
+    st = PreflightTraceStruct(cycles.ctypes.data, txns.ctypes.data if len(txns) else None,
+                              bigint.ctypes.data if len(bigint) else None, len(txns), len(bigint), int(pf.table_split_cycle))
+    return st, (cycles, txns, bigint)
+
+
+class DeviceTrace:
+    """a preflight trace resident on the device (r0b200_trace_upload), sorted there by (major, minor)"""
+
+    def __init__(self, hal, pf):
+        self.hal = hal
+        self.cycles = len(pf.cycles)
+        st, keep = _trace_struct(pf)
+        self._h = C.c_void_p()
+        check(hal._l.r0b200_trace_upload(hal._ctx, C.byref(st), C.c_uint32(self.cycles), C.byref(self._h)))
+        hal.sync()   # the host arrays may go away after this
+
+    def close(self):
+        if self._h:
+            self.hal._l.r0b200_trace_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Rv32imCircuitHal:
+    """CircuitWitnessGenerator + CircuitAccumulator for rv32im (rv32im/src/prove/hal/mod.rs:82-102) on the device"""
+
+    PARALLEL, SEQ_FORWARD, SEQ_REVERSE = 0, 1, 2
+
+    def __init__(self, hal):
+        self.hal = hal
+
+    def generate_witness(self, mode, trace, global_buf, data_buf):
+        check(self.hal._l.r0b200_witgen_rv32im(self.hal._ctx, C.c_uint32(mode), trace._h, global_buf.ptr, data_buf.ptr))
+
+    def step_accum(self, trace, data_buf, accum_buf, global_buf, mix_buf):
+        check(self.hal._l.r0b200_accum_rv32im(self.hal._ctx, trace._h, data_buf.ptr, accum_buf.ptr, global_buf.ptr,
+                                              mix_buf.ptr))
+
+
+class WitnessGenerator:
+    """prove/witgen/mod.rs:90-224 over the device Hal: new() = INVALID fill + injector scatter + generate_witness +
+    zeroize; accum(mix) = step_accum + zeroize. Buffers stay on the device."""
+
+    N_CODE, N_DATA, N_ACCUM, N_GLOBAL, N_MIX = 1, 211, 103, 90, 36
+
+    def __init__(self, hal, pf, mode=Rv32imCircuitHal.PARALLEL):
+        self.hal, self.pf = hal, pf
+        self.circuit = Rv32imCircuitHal(hal)
+        self.cycles = len(pf.cycles)
+        self.trace = DeviceTrace(hal, pf)
+        self.global_ = hal.copy_from_elem("global", pf.global_)
+        self.code = hal.alloc_elem_init("code", self.cycles * self.N_CODE, INVALID)
+        self.data = hal.alloc_elem_init("data", self.cycles * self.N_DATA, INVALID)
+        index, offsets, values = pf.injector
+        hal.scatter(self.data, index, offsets, values)
+        self.circuit.generate_witness(mode, self.trace, self.global_, self.data)
+        hal.eltwise_zeroize_elem(self.global_)
+        hal.eltwise_zeroize_elem(self.code)
+        hal.eltwise_zeroize_elem(self.data)
+        self.accum_buf = hal.alloc_elem_init("accum", self.cycles * self.N_ACCUM, INVALID)
+
+    def accum(self, mix):
+        mix_buf = self.hal.copy_from_elem("mix", mix)
+        self.circuit.step_accum(self.trace, self.data, self.accum_buf, self.global_, mix_buf)
+        self.hal.eltwise_zeroize_elem(self.accum_buf)
+        return mix_buf
+
+
 class SegmentProver:
     """Host-side mirror of `SegmentProver::prove_core`'s prove_inner block for rv32im
     (risc0/circuit/rv32im/src/prove/hal/mod.rs:171-222) over r0b200_prove_rv32im: commit code/data/accum, eval_check,
@@ -407,6 +493,23 @@ class SegmentProver:
 
     def abort(self, proof):
         self.hal._l.r0b200_prove_abort(proof)
+
+    def prove_core(self, pf):
+        """SegmentProverImpl::prove_core (rv32im/src/prove/hal/mod.rs:143-224) from a PreflightResults, everything on
+        the device in one call (r0b200_prove_segment_rv32im). Returns (seal, roots, query positions, globals)."""
+        hal = self.hal
+        st, keep = _trace_struct(pf)
+        index, offsets, values = (_u32(a) for a in pf.injector)
+        glob = _u32(pf.global_)
+        glob_out = np.zeros(90, dtype=np.uint32)
+        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
+        check(hal._l.r0b200_prove_segment_rv32im(
+            hal._ctx, hal.hash, C.c_uint32(pf.po2), C.byref(st), _np_ptr(glob), _np_ptr(index), C.c_size_t(index.size),
+            _np_ptr(offsets), _np_ptr(values), None, C.c_size_t(0), None, None, _np_ptr(self._seal),
+            C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots), C.c_size_t(16), C.byref(nroots),
+            _np_ptr(self._qpos), _np_ptr(glob_out)))
+        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
+                self._qpos.copy(), glob_out)
 
     def prove_uploaded(self, uploaded, glob):
         hal = self.hal

@@ -1,0 +1,149 @@
+"""CPU: the witness path's host side and the generated step functions, against the reference's own code.
+
+  * risc0_b200.preflight (restatement of execute/ + prove/witgen/preflight.rs) is pinned by the reference's golden
+    vectors for the memory image (binfmt/src/image.rs:503-546: 23 zero-subtree digests, image id of a one-word program)
+    and, much more strongly, by the reference's OWN compiled witness generator (oracle/_ref/librv32im_witgen_ref.so =
+    rv32im-sys/kernels/cxx/{steps.cpp,ffi.cpp}): it throws on any txn / cycle / paging / eqz inconsistency, so a trace
+    it accepts is a trace the circuit accepts;
+  * the witness it produces satisfies every constraint of the circuit (reference-compiled poly_fp, row by row);
+  * the step functions generated from the circuit IR (tools/gen_witgen.py; here in a host build) give the reference's
+    data and accum matrices word for word - the same text is what csrc/witgen*.cu compiles for the device.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import witgen_ref as W
+from risc0_b200 import preflight as PF
+
+pytestmark = pytest.mark.skipif(not (W.have_ref() and O.have_ref()), reason="oracle/_ref not built")
+
+
+def hexd(d):
+    return "".join("%08x" % int.from_bytes(int(w).to_bytes(4, "little"), "big") for w in d)
+
+
+def test_memory_image_golden_vectors():
+    # binfmt/src/image.rs:503-531 poseidon2_zeros (first and last three of the 23) and :533-546 image_circuit_match
+    z = PF.zero_digests()
+    assert hexd(z[0]) == "f85c5a32ccc45c22f9686b08d710d4597d7ce256cdcd63146426270d9432c644"
+    assert hexd(z[1]) == "2ce7714c40af126c2e86f320b10de417eddd8f51d2b9133d3105c3541a154812"
+    assert hexd(z[11]) == "adba743a459eb5357487a1238a0c4c238b8313458283900447e9b8540adfb042"
+    assert hexd(z[21]) == "e053c93b359c8905c5d8523139988b0ed4ef3426864a80498dfcb91d9b813364"
+    assert hexd(z[22]) == "242ce034cc4e9326f8b7071124454b2be1a1cd5d21b6483c7ff81d4ba5ac9566"
+    img = PF.MemoryImage.new_kernel(0x10000, {0x10000: 0x1234b337})
+    assert hexd(img.get_digest(0x0040_0100)) == "242ce034cc4e9326f8b7071124454b2be1a1cd5d21b6483c7ff81d4ba5ac9566"
+    assert hexd(img.image_id()) == "9d41290fa400705127c0240cb646586cc6ea8a23d560aa57cfa86c1369d9d53f"
+
+
+def mixes(seed):
+    rng = np.random.default_rng(seed)
+    return O.rand_elems(rng, 36), O.rand_ext(rng)
+
+
+def check_segment(seg, rand_z=(5, 6, 7, 8), seed=1):
+    pf = PF.PreflightResults(seg, rand_z)
+    glob, data = W.ref_generate_witness(pf)            # the reference accepts the trace
+    glob2, data2 = W.host_generate_witness(pf)         # generated step_Top == reference step_Top
+    assert np.array_equal(glob, glob2) and np.array_equal(data, data2)
+    mix, poly_mix = mixes(seed)
+    accum = W.ref_accum(pf, glob, data, mix)
+    assert np.array_equal(accum, W.host_accum(pf, glob, data, mix))
+    assert O.rv32im_check_constraints(accum, data, mix, glob, poly_mix, pf.po2) == (0, None)
+    return pf, glob, data, accum
+
+
+def test_loop_guest_terminating_segment():
+    # execute/testutil.rs:152-161 kernel::simple_loop, the reference's own witgen test guest (witgen/tests.rs:58-61)
+    segs = PF.execute(PF.simple_loop_kernel(200), segment_po2=14)
+    assert len(segs) == 1 and segs[0].po2 == 13 and segs[0].terminate_state == (0, 0)
+    assert segs[0].paging_cycles == 1821   # rv32im/examples/rv32im.rs:43
+    pf, glob, data, accum = check_segment(segs[0])
+    assert pf.table_split_cycle + PF.RESERVED_CYCLES <= pf.rows
+    # a tampered cell or an accum built from another mix breaks constraints (why prove_begin returns the mix first)
+    mix, poly_mix = mixes(1)
+    bad = data.copy()
+    bad[7 * pf.rows + 300] ^= 1
+    assert O.rv32im_check_constraints(accum, bad, mix, glob, poly_mix, pf.po2)[0] > 0
+    other = W.ref_accum(pf, glob, data, mixes(2)[0])
+    assert O.rv32im_check_constraints(other, data, mix, glob, poly_mix, pf.po2)[0] > 0
+
+
+def test_loop_guest_split_segments():
+    # fwd_rev_ab_split's shape (witgen/tests.rs:132-135): the session does not fit one segment, so the first segment is
+    # cut at the threshold (non-terminating: shutdownCycle / diff_count bookkeeping of fini) and the second resumes
+    segs = PF.execute(PF.simple_loop_kernel(4000), segment_po2=13)
+    assert len(segs) >= 2 and segs[0].terminate_state is None and segs[-1].terminate_state == (0, 0)
+    assert segs[0].post_state == segs[1].pre_state
+    for i, seg in enumerate(segs[:2]):
+        check_segment(seg, seed=10 + i)
+
+
+def all_insn_guest():
+    """every RV32IM instruction kind, byte/half/word memory traffic at all alignments, taken and untaken branches,
+    jal / jalr, fence, and a host read (NullSyscall pattern) - a multi_read-like kernel-mode guest (testutil.rs:163-184)"""
+    t0, t1, t2, t3, t4 = 5, 6, 7, 28, 29
+    a = PF.Assembler()
+    a.li(t0, 0x00500000)          # data pointer (kernel mode may touch any address above the zero page)
+    a.li(t1, 0x89abcdef)
+    a.li(t2, 0x00001234)
+    a.sw(t1, t0, 0)
+    a.store(1, t2, t0, 6)         # sh
+    a.store(0, t1, t0, 9)         # sb
+    for f3, off in ((0, 0), (0, 3), (1, 2), (2, 0), (4, 1), (5, 6)):   # lb lb lh lw lbu lhu
+        a.load(f3, t3, t0, off)
+    for f7, f3 in ((0, 0), (32, 0), (0, 4), (0, 6), (0, 7), (0, 2), (0, 3), (0, 1), (0, 5), (32, 5),
+                   (1, 0), (1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (1, 7)):
+        a.op(f7, f3, t4, t1, t2)
+    a.op(1, 4, t4, t1, 0)         # div by zero
+    a.op(1, 6, t4, t1, 0)         # rem by zero
+    for f3, imm in ((0, -5), (4, 0x7ff), (6, 0x0f0), (7, 0x555), (2, -1), (3, 7), (1, 13), (5, 3), (5, 0x400 | 7)):
+        a.opi(f3, t4, t1, imm)    # addi xori ori andi slti sltiu slli srli srai
+    a.lui(t3, 0xabcde)
+    a.text.append((0x12345 << 12) | (t3 << 7) | 0b0010111)   # auipc
+    a.beq(t1, t1, 8)              # taken: skips the next word
+    a.text.append(0)              # never executed (would be an illegal instruction)
+    a.bne(t1, t1, 8)              # not taken
+    a.blt(t2, t1, 8)              # signed: 0x1234 < negative? no
+    a._b(8, t1, t2, 5)            # bge
+    a.text.append(0)
+    a._b(8, t1, t2, 6)            # bltu taken
+    a.text.append(0)
+    a._b(8, t2, t1, 7)            # bgeu taken
+    a.text.append(0)
+    a.text.append((8 << 20) | (1 << 7) | 0b1101111)           # jal ra, +8
+    a.text.append(0)
+    a.text.append(0x0000000f)     # fence
+    pc_here = PF.USER_START_ADDR + 4 + 4 * len(a.text)
+    a.li(t3, pc_here + 16)        # li = lui + addi (2 words), then jalr (1 word), then a skipped word
+    a._i(0, t3, 0, 1, 0b1100111)  # jalr ra, 0(t3)
+    a.text.append(0)
+    for ptr, ln in ((0x00500100, 0), (0x00500101, 1), (0x00500103, 7), (0x00500200, 19), (0x00500302, 40)):
+        a.host_ecall_read(0, ptr, ln)
+        if ln:
+            a.lb(t3, t0, (ptr - 0x00500000) & 0x7ff)
+    a.host_terminate(0, 0)
+    entry, image = a.program()
+    return PF.MemoryImage.new_kernel(entry, image)
+
+
+def test_every_instruction_kind_and_host_read():
+    segs = PF.execute(all_insn_guest(), segment_po2=14)
+    assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
+    pf, _, _, _ = check_segment(segs[0], seed=3)
+    majors = set(zip(pf.cycles["major"].tolist(), pf.cycles["minor"].tolist()))
+    # misc0..2, mul0, div0, mem0, mem1, control (resume, fence), ecall (machine, terminate, read setup/bytes/words), poseidon
+    for want in [(0, 0), (0, 7), (1, 5), (2, 3), (2, 4), (2, 5), (2, 6), (3, 2), (4, 4), (5, 2), (6, 0), (6, 2), (7, 2), (8, 0), (8, 1),
+                 (8, 2), (8, 4), (8, 5), (9, 0)]:
+        assert want in majors, want
+
+
+def test_injector_and_globals_shape():
+    segs = PF.execute(PF.simple_loop_kernel(50), segment_po2=13)
+    pf = PF.PreflightResults(segs[0], (1, 2, 3, 4))
+    index, offsets, values = pf.injector
+    assert index.size == pf.rows + 1 and index[-1] == offsets.size == values.size
+    assert len(set(offsets.tolist())) == offsets.size          # one writer per cell: scatter order is irrelevant
+    assert int(values.max()) < PF.P
+    assert pf.cycles.dtype.itemsize == 36 and pf.txns.dtype.itemsize == 20   # rv32im-sys/src/lib.rs:21-61
+    assert (pf.global_ == 0xFFFFFFFF).sum() > 0                # output cells are left for the witness generator
