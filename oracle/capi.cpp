@@ -432,17 +432,39 @@ extern "C" const char* orc_verify_hello(int hash_kind, const uint32_t* seal, uin
 }
 
 // rv32im seal: Merkle / FRI / DEEP consistency (constraint evaluation needs the missing poly_ext.rs blob).
-extern "C" const char* orc_verify_rv32im(int hash_kind, const uint32_t* seal, uint64_t n, uint32_t* roots_out,
-                                         uint64_t* nroots) {
+// CircuitCoreDef::poly_ext supplied by the caller (verify/mod.rs:555-556 -> adapter.rs): evaluates the circuit's
+// constraint polynomial at the extension-field tap evaluations. tests/poly_ext_ir.py implements it from the committed
+// circuit IR (rv32im's own poly_ext.rs is a missing blob in the reference snapshot; the IR is the same polynomial,
+// parsed from the reference's poly_fp and pinned against its compiled form point by point).
+typedef void (*poly_ext_cb_t)(const uint32_t* poly_mix, const uint32_t* eval_u, uint64_t ntaps, const uint32_t* out,
+                              uint64_t nout, const uint32_t* mix, uint64_t nmix, uint32_t* result);
+static PolyExtFn wrap_poly_ext(poly_ext_cb_t cb) {
+  if (!cb) return PolyExtFn();
+  return [cb](FpExt poly_mix, const std::vector<FpExt>& eval_u, const std::vector<std::vector<Fp>>& args) {
+    uint32_t res[4] = {0, 0, 0, 0};
+    cb((const uint32_t*)&poly_mix, (const uint32_t*)eval_u.data(), eval_u.size(), (const uint32_t*)args[0].data(),
+       args[0].size(), (const uint32_t*)args[1].data(), args[1].size(), res);
+    return FpExt(Fp::raw(res[0]), Fp::raw(res[1]), Fp::raw(res[2]), Fp::raw(res[3]));
+  };
+}
+
+extern "C" const char* orc_verify_rv32im_ext(int hash_kind, const uint32_t* seal, uint64_t n, uint32_t* roots_out,
+                                             uint64_t* nroots, poly_ext_cb_t poly_ext, int* validity_checked) {
   ORC_TRY
   HashSuite suite = suite_of(hash_kind);
   TapSet taps = rv32im_taps();
   if (n == 0 || seal[0] != RV32IM_SEAL_VERSION) throw VerifyError("bad seal version word");
   Verifier* v = nullptr;
-  verify_standard(taps, suite, seal, n, RV32IM_CIRCUIT_INFO, RV32IM_OUTPUT_SIZE, RV32IM_MIX_SIZE, 1, PolyExtFn(), &v);
+  verify_standard(taps, suite, seal, n, RV32IM_CIRCUIT_INFO, RV32IM_OUTPUT_SIZE, RV32IM_MIX_SIZE, 1,
+                  wrap_poly_ext(poly_ext), &v);
   if (nroots) *nroots = v->roots.size();
   if (roots_out) memcpy(roots_out, v->roots.data(), v->roots.size() * 32);
+  if (validity_checked) *validity_checked = v->validity_checked ? 1 : 0;
   ORC_CATCH
+}
+extern "C" const char* orc_verify_rv32im(int hash_kind, const uint32_t* seal, uint64_t n, uint32_t* roots_out,
+                                         uint64_t* nroots) {
+  return orc_verify_rv32im_ext(hash_kind, seal, n, roots_out, nroots, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------ recursion circuit
@@ -544,16 +566,22 @@ extern "C" const char* orc_prove_recursion(int hash_kind, uint32_t po2, const ui
 }
 
 // recursion seal: Merkle / FRI / DEEP consistency (poly_ext.rs is present in the reference but not restated here)
-extern "C" const char* orc_verify_recursion(int hash_kind, const uint32_t* seal, uint64_t n, uint32_t* roots_out,
-                                            uint64_t* nroots) {
+extern "C" const char* orc_verify_recursion_ext(int hash_kind, const uint32_t* seal, uint64_t n, uint32_t* roots_out,
+                                                uint64_t* nroots, poly_ext_cb_t poly_ext, int* validity_checked) {
   ORC_TRY
   HashSuite suite = suite_of(hash_kind);
   TapSet taps = recursion_taps();
   Verifier* v = nullptr;
-  verify_standard(taps, suite, seal, n, RECURSION_CIRCUIT_INFO, RECURSION_OUTPUT_SIZE, RECURSION_MIX_SIZE, 0, PolyExtFn(), &v);
+  verify_standard(taps, suite, seal, n, RECURSION_CIRCUIT_INFO, RECURSION_OUTPUT_SIZE, RECURSION_MIX_SIZE, 0,
+                  wrap_poly_ext(poly_ext), &v);
   if (nroots) *nroots = v->roots.size();
   if (roots_out) memcpy(roots_out, v->roots.data(), v->roots.size() * 32);
+  if (validity_checked) *validity_checked = v->validity_checked ? 1 : 0;
   ORC_CATCH
+}
+extern "C" const char* orc_verify_recursion(int hash_kind, const uint32_t* seal, uint64_t n, uint32_t* roots_out,
+                                            uint64_t* nroots) {
+  return orc_verify_recursion_ext(hash_kind, seal, n, roots_out, nroots, nullptr, nullptr);
 }
 
 extern "C" void orc_free_str(char* s) { free(s); }

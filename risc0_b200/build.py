@@ -57,6 +57,24 @@ def generate(force=False):
                 raise RuntimeError("generator failed:\n%s\n%s" % (r.stdout, r.stderr))
 
 
+def generate_witgen(force=False):
+    """(re)create csrc/gen/witgen_rv32im.inc from the committed witgen circuit IR (tools/gen_witgen.py)"""
+    root = os.path.join(HERE, "..")
+    gen = os.path.join(root, "tools", "gen_witgen.py")
+    irf = os.path.join(HERE, "circuits", "rv32im_witgen.ir.json.gz")
+    out = os.path.join(CSRC, "gen", "witgen_rv32im.inc")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(gen), os.path.getmtime(irf)):
+        r = subprocess.run([sys.executable, gen], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("witgen generator failed:\n%s\n%s" % (r.stdout, r.stderr))
+
+
+# The two kernels that instantiate the generated rv32im step functions are 19 k lines of branchy straight-line code:
+# ptxas -O3 needs 10+ minutes for them and gains nothing measurable (they are latency / divergence bound), -O1 needs two.
+SLOW_SOURCES = {"witgen_step_exec.cu": ["-Xptxas", "-O1", "-diag-suppress", "550"],
+                "witgen_step_accum.cu": ["-Xptxas", "-O1", "-diag-suppress", "550"]}
+
+
 def _ptxas(ptx, cubin, flags):
     cmd = [os.path.join(os.path.dirname(NVCC), "ptxas"), "-arch=sm_100a", "-v"] + flags + [ptx, "-o", cubin]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -87,7 +105,7 @@ def _assemble(ptx, cubin, verbose):
 
 
 def _compile(src, obj, verbose):
-    cmd = [NVCC] + FLAGS + ["-I", CSRC, "-c", src, "-o", obj]
+    cmd = [NVCC] + FLAGS + SLOW_SOURCES.get(os.path.basename(src), []) + ["-I", CSRC, "-c", src, "-o", obj]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -100,13 +118,18 @@ def build(force=False, verbose=False, jobs=None):
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     generate(force)
-    hdr_time = max(os.path.getmtime(h) for h in headers())
+    generate_witgen(force)
+    wg_only = {"witgen_rt.cuh", "witgen_rv32im.inc"}   # headers only the witgen translation units include
+    hdr_time = max(os.path.getmtime(h) for h in headers() if os.path.basename(h) not in wg_only)
+    wg_time = max(os.path.getmtime(h) for h in headers() + [os.path.join(CSRC, "gen", "witgen_rv32im.inc")])
     todo, objs = [], []
     for src in sources():
         obj = os.path.join(OBJ, os.path.relpath(src, CSRC).replace(os.sep, "_")[:-3] + ".o")
         objs.append(obj)
-        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+        dep_time = wg_time if os.path.basename(src).startswith("witgen") else hdr_time
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), dep_time):
             todo.append((src, obj))
+    todo.sort(key=lambda so: os.path.basename(so[0]) not in SLOW_SOURCES)   # start the slow ones first
     # generated PTX kernels -> cubins, embedded as read-only data (symbol r0_cubin_<file stem>)
     ptx_todo, cubins = [], []
     # the ptxas flag set is part of the cubin staleness key

@@ -5,7 +5,9 @@
 #include "witgen_rt.cuh"
 
 namespace r0wg {
+namespace {   // internal linkage: both step translation units instantiate the same generated functions
 #include "gen/witgen_rv32im.inc"
+}  // namespace
 
 __global__ void __launch_bounds__(128) k_step_exec(const WShared* s, const uint32_t* order, uint32_t begin, uint32_t count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -434,6 +434,21 @@ def verify_recursion(seal, kind=POSEIDON2):
     return roots[:8 * nr.value].reshape(-1, 8).copy()
 
 
+def verify_with_validity(seal, circuit="rv32im", kind=POSEIDON2):
+    """the restated verifier INCLUDING the constraint check check(z) * ((3z)^N - 1) == poly_ext(eval_u)
+    (verify/mod.rs:370-390), poly_ext evaluated from the committed circuit IR (tests/poly_ext_ir.py).
+    Returns (roots, validity_checked); raises on any failed check."""
+    import poly_ext_ir
+    seal = u32(seal)
+    roots = np.zeros(8 * 16, dtype=np.uint32)
+    nr = _u64(0)
+    checked = C.c_int(0)
+    fn = lib().orc_verify_rv32im_ext if circuit == "rv32im" else lib().orc_verify_recursion_ext
+    _check(fn(kind, ptr(seal), _u64(len(seal)), ptr(roots), C.byref(nr), poly_ext_ir.poly_ext(circuit).callback(),
+              C.byref(checked)))
+    return roots[:8 * nr.value].reshape(-1, 8).copy(), bool(checked.value)
+
+
 def synthetic_witness_recursion(po2, seed=None):
     """same generator as synthetic_witness, recursion shapes; the control columns are random too (the prover never
     checks constraint satisfaction)"""

@@ -1,0 +1,112 @@
+"""GPU parity of the witness path: the device witness generator / accumulator (csrc/witgen*.cu, generated step
+functions) against the REFERENCE'S OWN compiled C++ witgen on the same preflight trace, word for word; then the whole
+prove_core from a preflight trace (everything on the device) against the CPU prover fed with the reference witness.
+Traces come from risc0_b200.preflight (tests/test_preflight.py pins that on the CPU)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import witgen_ref as W
+from risc0_b200 import B200Hal, SegmentProver, WitnessGenerator
+from risc0_b200 import preflight as PF
+from test_preflight import all_insn_guest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (W.have_ref() and O.have_ref()), reason="oracle/_ref not built")]
+
+
+@pytest.fixture(scope="module")
+def hal():
+    h = B200Hal(0, "poseidon2")
+    yield h
+    h.close()
+
+
+def segments():
+    out = {"loop_po2_13": PF.execute(PF.simple_loop_kernel(200), segment_po2=14)[0],
+           "all_insn": PF.execute(all_insn_guest(), segment_po2=14)[0]}
+    split = PF.execute(PF.simple_loop_kernel(4000), segment_po2=13)
+    out["split_first"], out["split_second"] = split[0], split[1]
+    return out
+
+
+SEGS = None
+
+
+def seg(name):
+    global SEGS
+    if SEGS is None:
+        SEGS = segments()
+    return SEGS[name]
+
+
+@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second"])
+def test_device_witgen_and_accum_match_reference(hal, name):
+    pf = PF.PreflightResults(seg(name), (11, 12, 13, 14))
+    want_glob, want_data = W.ref_generate_witness(pf)
+    wg = WitnessGenerator(hal, pf)
+    assert np.array_equal(wg.global_.view(), want_glob)
+    assert np.array_equal(wg.data.view(), want_data)
+    assert not wg.code.view().any()
+    rng = np.random.default_rng(5)
+    mix = O.rand_elems(rng, 36)
+    wg.accum(mix)
+    assert np.array_equal(wg.accum_buf.view(), W.ref_accum(pf, want_glob, want_data, mix))
+
+
+def test_device_witgen_reports_bad_traces(hal):
+    pf = PF.PreflightResults(seg("loop_po2_13"), (1, 2, 3, 4))
+    bad = PF.PreflightResults(seg("loop_po2_13"), (1, 2, 3, 4))
+    bad.txns = bad.txns.copy()
+    bad.txns["addr"][len(bad.txns) // 2] ^= 4        # "memory peek not in preflight"
+    with pytest.raises(Exception) as ei:
+        WitnessGenerator(hal, bad)
+    assert "witgen" in str(ei.value)
+    with pytest.raises(Exception):                   # the reference throws on the same trace
+        W.ref_generate_witness(bad)
+    WitnessGenerator(hal, pf)                        # the context is still usable afterwards
+
+
+@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first"])
+def test_prove_core_from_trace_bit_exact_and_valid(hal, name):
+    pf = PF.PreflightResults(seg(name), (21, 22, 23, 24))
+    po2 = pf.po2
+    seal, roots, qpos, glob = SegmentProver(hal).prove_core(pf)
+    # CPU side: reference witgen -> oracle transcript up to the mix -> reference accum from THAT mix -> oracle prover
+    want_glob, data = W.ref_generate_witness(pf)
+    code = np.zeros(pf.rows, dtype=np.uint32)
+    mix = O.prove_rv32im_mix(po2, code, data, want_glob)
+    accum = W.ref_accum(pf, want_glob, data, mix)
+    want_seal, want_roots, want_qpos = O.prove_rv32im(po2, code, data, accum, want_glob)
+    assert np.array_equal(glob, want_glob)
+    assert np.array_equal(roots, want_roots) and np.array_equal(qpos, want_qpos)
+    assert np.array_equal(seal, want_seal)
+    # the restated verifier accepts it INCLUDING the constraint check check(z) * ((3z)^N - 1) == poly_ext(eval_u)
+    vroots, validity_checked = O.verify_with_validity(seal)
+    assert validity_checked and np.array_equal(vroots, roots)
+    # and this is a witness the circuit accepts: every constraint vanishes on every row
+    assert O.rv32im_check_constraints(accum, data, mix, want_glob, O.rand_ext(np.random.default_rng(1)), po2) == (0, None)
+
+
+def test_two_phase_with_device_accum(hal):
+    # the protocol-correct flow through the Hal-level API: begin -> mix -> step_accum on the device -> finish
+    pf = PF.PreflightResults(seg("loop_po2_13"), (31, 32, 33, 34))
+    wg = WitnessGenerator(hal, pf)
+    glob = wg.global_.view()
+    prover = SegmentProver(hal)
+    h, mix = prover.begin(pf.po2, wg.code, wg.data, glob)
+    wg.accum(mix)
+    seal, roots, _ = prover.finish(h, wg.accum_buf)
+    want = SegmentProver(hal).prove_core(pf)[0]
+    assert np.array_equal(seal, want)
+
+
+def test_verifier_rejects_a_witness_that_violates_constraints(hal):
+    # a synthetic (random) witness gives a seal whose Merkle / FRI / DEEP checks pass but whose constraint check fails:
+    # the validity check is what distinguishes the two
+    po2 = 10
+    code, data, accum, glob = O.synthetic_witness(po2)
+    seal, _, _ = SegmentProver(hal).prove(po2, code, data, accum, glob)
+    O.verify_rv32im(seal)
+    with pytest.raises(Exception) as ei:
+        O.verify_with_validity(seal)
+    assert "constraint" in str(ei.value)

@@ -147,3 +147,22 @@ def test_injector_and_globals_shape():
     assert int(values.max()) < PF.P
     assert pf.cycles.dtype.itemsize == 36 and pf.txns.dtype.itemsize == 20   # rv32im-sys/src/lib.rs:21-61
     assert (pf.global_ == 0xFFFFFFFF).sum() > 0                # output cells are left for the witness generator
+
+
+def test_cpu_prover_seal_of_a_real_witness_passes_the_full_verifier():
+    # reference witgen -> oracle prover -> restated verifier with the validity check (poly_ext from the circuit IR)
+    seg = PF.execute(PF.simple_loop_kernel(100), segment_po2=14)[0]
+    pf = PF.PreflightResults(seg, (1, 2, 3, 4))
+    glob, data = W.ref_generate_witness(pf)
+    code = np.zeros(pf.rows, dtype=np.uint32)
+    mix = O.prove_rv32im_mix(pf.po2, code, data, glob)
+    accum = W.ref_accum(pf, glob, data, mix)
+    seal, roots, _ = O.prove_rv32im(pf.po2, code, data, accum, glob)
+    vroots, checked = O.verify_with_validity(seal)
+    assert checked and np.array_equal(vroots, roots)
+    # accum computed from a mix other than the transcript's: same Merkle / FRI structure, constraint check fails
+    bad_accum = W.ref_accum(pf, glob, data, mixes(9)[0])
+    bad_seal, _, _ = O.prove_rv32im(pf.po2, code, data, bad_accum, glob)
+    O.verify_rv32im(bad_seal)
+    with pytest.raises(Exception):
+        O.verify_with_validity(bad_seal)
