@@ -1,18 +1,23 @@
 #!/usr/bin/env python3
 """Headline benchmark: proved rv32im cycles per second, po2 = 20 segments (BASELINE.json configs[1]).
 
-One "step" = one full segment proof (commit code/data/accum -> eval_check -> DEEP -> FRI -> seal) of a synthetic
-po2 = 20 witness (every cell uniform in [0, P), code column zero) through the C ABI
-(r0b200_prove_rv32im). With N ranks every rank proves its own segment each step (segments are independent: weak
+One "step" = one whole `prove_core` (rv32im/src/prove/hal/mod.rs:143-224) of a full po2 = 20 segment of the reference's
+loop guest (execute/testutil.rs kernel::simple_loop, the datasheet's workload), starting from its PreflightResults
+(preflight trace + injector + globals, produced once in setup by risc0_b200.preflight): witness generation on the
+device, commit code / data, mix draw, accum from that mix on the device, commit accum, eval_check, DEEP, FRI -> seal.
+The witness is real: it satisfies every constraint of the circuit and the seal passes the restated verifier including
+its validity check (tests/). With N ranks every rank proves its own segment each step (segments are independent: weak
 scaling, no data-path collective); torch.distributed (NCCL) is used only for the barrier and the max-over-ranks time.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--po2 20] [--impl reference]
 
-value  : witness resident in HBM when the timed region starts.
-e2e    : witness in pinned HOST memory, H2D copies + seal D2H inside the timed region (what a caller of the plugin sees).
+value  : the segment (trace, injector, globals) resident in HBM when the timed region starts (r0b200_prove_segment).
+e2e    : the segment in pinned HOST memory; every step's H2D copy (r0b200_segment_upload, on the copy stream, one segment
+         ahead - the reference's depth-2 worker queue) and seal D2H are inside the timed region.
 roofline: the dominant kernel family of the step, timed live with CUDA events on the prover's stream.
-cpu_baseline / --impl reference: the CPU prover (oracle restatement of CpuHal + the reference's own compiled poly_fp)
-on the box's host cores, on a bounded sample (a smaller segment), reported beside it - not the target.
+cpu_baseline / --impl reference: the CPU prove_core on the box's host cores from the same kind of PreflightResults: the
+reference's own compiled C++ witgen / accum + the oracle port of CpuHal / Prover + the reference-compiled poly_fp, on a
+bounded sample (a smaller segment), reported beside it - not the target.
 """
 import argparse
 import json
@@ -27,12 +32,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-USER_CYCLES = {20: 1013346}  # full po2=20 loop segment: (1024*494+817) iterations x 2 insns (datasheet.rs:58)
+RAND_Z = (0x1234567, 0x89abcd, 0x3141592, 0x2718281)   # fixed instead of the reference's rand::rng() (hal/mod.rs:136-137)
 
 
-def user_cycles(po2):
-    # reserved (4113) + paging (~1821) cycles are not user cycles; same overhead assumed at other sizes
-    return USER_CYCLES.get(po2, max((1 << po2) - 4113 - 1821, 1))
+def build_segment(po2):
+    """PreflightResults of the first (full, non-terminating) po2-sized segment of the loop guest: what
+    SegmentProver::preflight hands to prove_core. Plain-Python executor + preflight: ~30 s at po2 = 20 (setup only)."""
+    from risc0_b200 import preflight as PF
+    seg = PF.execute(PF.simple_loop_kernel(1 << 30), segment_po2=po2, max_segments=1, max_cycles=1 << 40)[0]
+    return PF.PreflightResults(seg, RAND_Z)
 
 
 def synthetic_witness(po2, seed):
@@ -95,6 +103,17 @@ def emit(line):
     print(json.dumps(line), flush=True)
 
 
+def cpu_prove_core(pf):
+    """CPU prove_core from a PreflightResults: the REFERENCE'S compiled C++ witgen / accum (oracle/_ref) + the oracle
+    port of CpuHal / Prover with the reference-compiled poly_fp. Returns the seal."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import witgen_ref as W
+    glob, data = W.ref_generate_witness(pf)
+    code = np.zeros(pf.rows, dtype=np.uint32)
+    return O.prove_rv32im_two_phase(pf.po2, code, data, glob, lambda mix: W.ref_accum(pf, glob, data, mix))[0]
+
+
 def run_reference(args, rank, world):
     """CPU prover on the host cores (rank 0 only). Each step proves one bounded-size segment."""
     if rank != 0:
@@ -104,27 +123,136 @@ def run_reference(args, rank, world):
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    po2 = args.cpu_po2
-    code, data, accum, glob = synthetic_witness(po2, 0x5EED0000 + po2)
+    # the headline size itself when the run is short enough for it (~90 s per po2 = 20 segment on 16 cores)
+    po2 = args.po2 if (args.steps + args.warmup) <= 2 else args.cpu_po2
+    pf = build_segment(po2)
     cores = O.lib().orc_num_threads()
     O.load_ref()
     for _ in range(args.warmup):
-        O.prove_rv32im(po2, code, data, accum, glob)
+        cpu_prove_core(pf)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.prove_rv32im(po2, code, data, accum, glob)
+        cpu_prove_core(pf)
     dt = time.perf_counter() - t0
-    value = args.steps * user_cycles(po2) / dt
-    sample = "po2=%d segment (%d cycles) per step; CPU prover = oracle port of CpuHal/Prover + reference-compiled poly_fp" % (po2, 1 << po2)
+    value = args.steps * pf.user_cycles / dt
+    sample = ("po2=%d loop-guest segment (%d cycles, %d user cycles) per step; CPU prove_core = reference-compiled C++ witgen + "
+              "accum, oracle port of CpuHal/Prover, reference-compiled poly_fp" % (po2, 1 << po2, pf.user_cycles))
     line = {"impl": "reference", "metric": "proved user-cycles/sec (rv32im po2=%d segments)" % args.po2, "value": value, "unit": "cycles/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "rv32im segment po2=%d full prove_segment (NTT + Poseidon2 Merkle + eval_check + DEEP + FRI)" % args.po2,
-                       "sample": "each step proves one po2=%d segment on the host cores (bounded sample of the po2=%d workload; "
-                                 "prover cost per cycle is flat in po2 up to the log factor)" % (po2, args.po2), "hash": "poseidon2"},
+            "config": {"workload": "rv32im segment po2=%d full prove_core from a preflight trace (witgen + accum + NTT + Poseidon2 "
+                                   "Merkle + eval_check + DEEP + FRI), loop guest" % args.po2,
+                       "sample": "each step proves one po2=%d segment on the host cores%s" % (
+                           po2, "" if po2 == args.po2 else " (bounded sample of the po2=%d workload; prover cost per cycle is "
+                           "flat in po2 up to the log factor)" % args.po2), "same_config": po2 == args.po2, "hash": "poseidon2"},
             "cpu_baseline": {"value": value, "unit": "cycles/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+class PinnedSegment:
+    """a PreflightResults whose arrays live in pinned host memory (so r0b200_segment_upload's copies are asynchronous)"""
+
+    def __init__(self, pf, torch):
+        self._keep = []
+
+        def pin(a):
+            a = np.ascontiguousarray(a)
+            t = torch.empty(max(a.nbytes, 16), dtype=torch.uint8).pin_memory()
+            v = t.numpy()[:a.nbytes].view(a.dtype).reshape(a.shape)
+            v[...] = a
+            self._keep.append(t)
+            return v
+
+        self.po2, self.rows, self.table_split_cycle, self.user_cycles = pf.po2, pf.rows, pf.table_split_cycle, pf.user_cycles
+        self.cycles, self.txns, self.bigint_bytes = pin(pf.cycles), pin(pf.txns), pf.bigint_bytes
+        self.injector = tuple(pin(a) for a in pf.injector)
+        self.global_ = pin(pf.global_)
+        self.h2d_bytes = (self.cycles.nbytes + self.txns.nbytes + sum(a.nbytes for a in self.injector) + self.global_.nbytes)
+
+
+def extra_configs(hal, torch, peak):
+    """BASELINE.json configs 3-5 as short runs after the timed region (N = 1 only): po2 = 22 segment, recursion proof,
+    NTT and Merkle sweeps against the HBM roofline. Synthetic matrices generated on the device."""
+    import ctypes as C
+    from risc0_b200 import SegmentProver
+    P = 15 * 2**27 + 1
+    out = {}
+
+    class Dev:
+        """hal-compatible view of a torch allocation (uniform [0, P) words = uniform Montgomery elements)"""
+
+        def __init__(self, n):
+            self.t = torch.randint(0, P, (n,), dtype=torch.int32, device="cuda")
+            self.n = n
+
+        @property
+        def ptr(self):
+            return C.c_void_p(self.t.data_ptr())
+
+        def size(self):
+            return self.n
+
+    def timeit(fn, iters=5, warm=2):
+        torch.cuda.synchronize()
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(iters):
+            hal.timer_start()
+            fn()
+            ts.append(hal.timer_stop())
+        return float(np.median(ts))
+
+    prover = SegmentProver(hal)
+    # config 4: recursion lift / join proofs are all one shape (po2 = 18); config 3: po2 = 22 segments
+    for name, circuit, po2 in (("recursion_po2_18", "recursion", 18), ("rv32im_po2_22", "rv32im", 22)):
+        c_code, c_data, c_accum, n_glob = prover.SHAPES[circuit]
+        n = 1 << po2
+        code, data, accum = Dev(c_code * n), Dev(c_data * n), Dev(c_accum * n)
+        if circuit == "rv32im":
+            code.t.zero_()
+        glob = np.arange(n_glob, dtype=np.uint32)
+        ms = timeit(lambda: prover.prove(po2, code, data, accum, glob, circuit=circuit), iters=3 if po2 < 20 else 1, warm=1)
+        out[name] = {"ms_per_proof": round(ms, 3), "witness": "synthetic (uniform random matrices, device-resident)",
+                     "cycles_per_s": round((n - 4113 - 1821) / ms * 1e3) if circuit == "rv32im" else None,
+                     "proofs_per_s": round(1e3 / ms, 2)}
+        del code, data, accum
+    # config 5: NTT sweep n = 2^16..2^24 x c in {1,4,16,64,211,256} (c*n*4 B*5 <= 64 GB), Merkle sweep
+    ntt = []
+    for lg in range(16, 25):
+        for c in (1, 4, 16, 64, 211, 256):
+            n = 1 << lg
+            if c * n * 4 * 5 > 64e9:
+                continue
+            x = Dev(n * c)
+            row = {"lg_n": lg, "cols": c}
+            ms = timeit(lambda: hal.batch_interpolate_ntt(x, c), iters=3, warm=1)
+            row["intt_GBps"] = round(8 * n * c / ms / 1e6, 1)
+            ms = timeit(lambda: hal.batch_bit_reverse(x, c), iters=3, warm=1)
+            row["bit_reverse_GBps"] = round(8 * n * c / ms / 1e6, 1)
+            if lg + 2 <= 24:
+                y = Dev(4 * n * c)
+                ms = timeit(lambda: hal.batch_expand_into_evaluate_ntt(y, x, c, 2), iters=3, warm=1)
+                row["expand_ntt_GBps"] = round(20 * n * c / ms / 1e6, 1)
+                del y
+            ntt.append(row)
+            del x
+    out["ntt_sweep"] = {"unit": "algorithmic GB/s (8cn iNTT / bit-reverse, 20cn expand+NTT)", "hbm_peak_GBps": peak, "cells": ntt}
+    merkle = []
+    for lg in range(16, 25, 2):
+        for c in (1, 16, 64, 103, 211, 256):
+            r = 1 << lg
+            if r * c * 4 > 20e9:
+                continue
+            m, nodes = Dev(r * c), Dev(16 * r)
+            ms = timeit(lambda: hal.merkle_build(nodes, m, r, c), iters=3, warm=1)
+            perms = r * ((c + 15) // 16) + r - 1
+            merkle.append({"lg_rows": lg, "cols": c, "ms": round(ms, 3), "GBps": round((4 * r * c + 32 * r + 96 * (r - 1)) / ms / 1e6, 1),
+                           "Gperm_per_s": round(perms / ms / 1e6, 3)})
+            del m, nodes
+    out["merkle_sweep"] = {"unit": "hash_rows + all fold levels; algorithmic GB/s and Poseidon2 permutations/s", "cells": merkle}
+    return out
 
 
 def main():
@@ -136,6 +264,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-po2", type=int, default=16, dest="cpu_po2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs 3-5 short runs (po2=22, recursion, sweeps)")
     ap.add_argument("--hash", default="poseidon2", choices=["poseidon2", "sha-256"],
                     help="hash suite (the reference's default for rv32im segments is poseidon2)")
     args = ap.parse_args()
@@ -144,7 +273,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        # K and W are honoured as given: one po2=16 sample segment takes ~5 s on 16 host cores
         run_reference(args, rank, world)
         return
 
@@ -160,7 +288,9 @@ def main():
     prover = SegmentProver(hal)
     po2 = args.po2
     n = 1 << po2
-    code, data, accum, glob = synthetic_witness(po2, 0x5EED0000 + po2 + 1000 * rank)
+    t_setup = time.perf_counter()
+    pf = PinnedSegment(build_segment(po2), torch)
+    t_setup = time.perf_counter() - t_setup
 
     def barrier():
         if world > 1:
@@ -173,10 +303,11 @@ def main():
     def max_over_ranks(x):
         return shard.max_over_ranks(x, device="cuda")
 
-    # ---- device-resident arm
-    d_code, d_data, d_accum = hal.copy_from_elem("code", code), hal.copy_from_elem("data", data), hal.copy_from_elem("accum", accum)
+    # ---- device-resident arm: the segment (trace, injector, globals) is in HBM; each step is one whole prove_core
+    resident = prover.upload_segment(pf)
+    hal.sync()
     for _ in range(args.warmup):
-        seal, _, _ = prover.prove(po2, d_code, d_data, d_accum, glob)
+        seal = prover.prove_segment(resident, free=False)[0]
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -184,35 +315,23 @@ def main():
     hal.profile_begin()
     hal.timer_start()
     for _ in range(args.steps):
-        seal, _, _ = prover.prove(po2, d_code, d_data, d_accum, glob)
+        seal = prover.prove_segment(resident, free=False)[0]
     ms = hal.timer_stop()
     phases = hal.profile_end()
     launches = hal.launch_count() - launches0
     barrier()
     ms = max_over_ranks(ms)
-    del d_code, d_data, d_accum
+    prover.free_segment(resident)
 
-    # ---- end-to-end arm: pinned host witness, H2D + seal D2H inside the timed region
-    def pinned(a):
-        t = torch.empty(a.size, dtype=torch.int32).pin_memory()
-        v = t.numpy().view(np.uint32)
-        v[:] = a
-        return t, v
-
-    keep = [pinned(code), pinned(data), pinned(accum)]
-    h_code, h_data, h_accum = (k[1] for k in keep)
-    # depth-2 pipeline, as the reference's worker queues do: the upload of step s+1's code + data is enqueued (copy
-    # stream) before step s is proved. accum cannot travel with them: it is a function of the mix that prove_begin
-    # draws after committing data (rv32im/src/prove/hal/mod.rs:209-217), so its H2D copy sits between the two
-    # phases of every step - on the critical path until step_accum runs on the device. Every step's H2D copies and
-    # seal D2H are inside the timed region.
+    # ---- end-to-end arm: the segment starts in pinned host memory every step. Depth-2 pipeline as the reference's
+    # worker queues do: the upload of step s+1 is enqueued on the copy stream before step s is proved. Every step's H2D
+    # copy and seal D2H are inside the timed region; nothing about a step exists on the device before its own upload.
     def e2e_steps(k):
-        up = prover.upload(po2, h_code, h_data, None)
+        up = prover.upload_segment(pf)
         out = None
         for s_ in range(k):
-            nxt = prover.upload(po2, h_code, h_data, None) if s_ + 1 < k else None
-            proof, _mix = prover.begin(po2, None, None, glob, uploaded=up)
-            out = prover.finish(proof, h_accum)[0]
+            nxt = prover.upload_segment(pf) if s_ + 1 < k else None
+            out = prover.prove_segment(up)[0]
             up = nxt
         return out
 
@@ -226,7 +345,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=3)
 
-    cycles = user_cycles(po2)
+    cycles = pf.user_cycles
     # every rank proved `steps` segments of `cycles` user cycles; whole-job value = all ranks' units / max time
     units = shard.gather_counts(args.steps * cycles, device="cuda")
     value = shard.whole_job_throughput(units, ms * 1e-3)
@@ -240,7 +359,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    # kernel families: the 45 generated eval_check part kernels are one family ("eval_check" brackets them)
+    # kernel families: the generated eval_check part kernels are one family ("eval_check" brackets them)
     families = {k: v for k, v in phases.items() if not k.startswith("eval_check_p")}
     top = max(families.items(), key=lambda kv: kv[1]["ms"])
     tname, t = top
@@ -253,32 +372,28 @@ def main():
     if tname == "eval_check":
         nlaunch = t["n"] * int(stats.get("parts", 1))     # every eval_check call launches all part kernels
     achieved = t["bytes"] / (t["ms"] * 1e-3) / 1e9 if t["ms"] > 0 else 0.0
-    # DRAM traffic per launch from the committed ncu --set full capture of this kernel family (profiles/), scaled by
-    # the number of domain points; null when no capture exists for the family
+    # DRAM traffic per launch from the committed ncu --set full capture of this kernel family (profiles/)
     traffic = None
     try:
-        if tname == "eval_check":
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r1_evalcheck_dram_traffic.json")))
-            per_point = [(v["dram_read_Mbyte"] + v["dram_write_Mbyte"]) * 1e6 / (1 << 18) for v in cap["kernels"].values()]
-            traffic = sum(per_point) / len(per_point) * (4 << po2)
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")))
+        if tname in cap:
+            traffic = cap[tname]["dram_bytes_per_launch_po2_20"] * (1 << po2) / (1 << 20)
     except Exception:
         traffic = None
-    roofline = {"bound": "hbm", "kernel": tname + (" (%d generated part kernels per step)" % (nlaunch // args.steps) if tname == "eval_check" else ""),
+    roofline = {"bound": "hbm", "bound_actual": "int32 (fma pipe) - see int32_roofline; the HBM fraction is low by construction",
+                "kernel": tname + (" (%d generated part kernels per step)" % (nlaunch // args.steps) if tname == "eval_check" else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "launches": nlaunch, "avg_launch_ms": t["ms"] / max(nlaunch, 1),
-                "share_of_step": t["ms"] / (ms if world == 1 else ms),
+                "share_of_step": t["ms"] / ms,
                 "note": "achieved = algorithmic bytes ((4*315+16) B per domain point for eval_check, 4*cols+32 B per row for "
                         "hash_rows) / summed device time of the family. Both are INT32-bound, not HBM-bound (Poseidon2: 1356 "
-                        "modmul per permutation; eval_check: ~270 k instructions per point, fma-heavy pipe at 59 % of the ceiling of its own multiply count, see int32_roofline), so "
-                        "the HBM fraction is low by construction; eval_check's DRAM traffic is ~20x algorithmic because every "
-                        "part kernel re-reads the tap columns it needs. See DESIGN.md 3.3/3.4 and profiles/."}
+                        "modmul per permutation; eval_check: ~270 k instructions per point). See DESIGN.md 3.3/3.4 and profiles/."}
     phase_ms = {k: round(v["ms"] / args.steps, 4) for k, v in sorted(phases.items(), key=lambda kv: -kv[1]["ms"])}
     phase_gbs = {k: round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) for k, v in phases.items() if v["ms"] > 0 and v["bytes"] > 0}
 
     # INT32 view of the same family: these kernels are bound by the fma pipe's quarter-rate wide multiplies
-    # (IMAD.WIDE / IMAD.HI: 4 cycles per warp instruction per sub-partition, IMAD: 2 - profiles/r1_int_pipe_rates.log),
-    # so the meaningful ceiling is fma-pipe cycles, not bytes
+    # (IMAD.WIDE / IMAD.HI: 4 cycles per warp instruction per sub-partition, IMAD: 2 - profiles/r1_int_pipe_rates.log)
     int32 = None
     sm_mhz = (sampler.result().get("sm_mhz") or 1965.0)
     smsp_cycles = 148 * 4 * sm_mhz * 1e6 * (t["ms"] * 1e-3)       # available sub-partition cycles during the family's time
@@ -288,38 +403,54 @@ def main():
         int32 = {"bound": "fma pipe (IMAD.WIDE 4 clk, IMAD 2 clk, IMAD.HI 4 clk per warp instruction per sub-partition)",
                  "wide_multiplies_per_point": stats["wide_multiplies"], "reductions_per_point": stats["reductions"],
                  "fma_cycles_needed": need, "smsp_cycles_available": smsp_cycles, "frac": need / smsp_cycles}
+    elif tname == "hash_rows":
+        perms = (4 << po2) * 23 * t["n"]                           # 1 + 14 + 7 + 1 sponge blocks per domain row
+        need = perms * 12.5e3 / 32.0                               # 852 x 10 + 504 x 8 fma-pipe cycles per permutation and warp lane group
+        int32 = {"bound": "fma pipe (Poseidon2: 852 Montgomery + 504 Shoup products per permutation)", "permutations": perms,
+                 "Gperm_per_s": perms / (t["ms"] * 1e-3) / 1e9, "fma_cycles_needed": need, "smsp_cycles_available": smsp_cycles,
+                 "frac": need / smsp_cycles}
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_lib as O
-        cp = args.cpu_po2
-        w = synthetic_witness(cp, 0x5EED0000 + cp)
-        O.load_ref()
-        t0 = time.perf_counter()
-        O.prove_rv32im(cp, *w)
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": user_cycles(cp) / dt, "unit": "cycles/s", "cores": O.lib().orc_num_threads(), "kind": "port",
-                        "sample": "one po2=%d segment (%d cycles, %.1f s): oracle port of CpuHal/Prover + reference-compiled poly_fp" % (cp, 1 << cp, dt)}
+    extras = None
+    if rank == 0 and world == 1:
+        if not args.no_extra:
+            try:
+                extras = extra_configs(hal, torch, peak)
+            except Exception as e:   # the headline line must survive a failure of the side runs
+                extras = {"error": repr(e)}
+        if not args.no_cpu_baseline:
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O
+            cp = args.cpu_po2
+            cpf = build_segment(cp)
+            O.load_ref()
+            t0 = time.perf_counter()
+            cpu_seal = cpu_prove_core(cpf)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": cpf.user_cycles / dt, "unit": "cycles/s", "cores": O.lib().orc_num_threads(), "kind": "port",
+                            "sample": "one po2=%d loop-guest segment (%d cycles, %d user cycles, %.1f s): reference-compiled C++ witgen "
+                                      "+ accum, oracle port of CpuHal/Prover, reference-compiled poly_fp" % (cp, 1 << cp, cpf.user_cycles, dt),
+                            "seal_words": int(len(cpu_seal))}
 
     if rank == 0:
-        h2d = (315 * n + 90) * 4
         line = {"metric": "proved user-cycles/sec (rv32im po2=%d segments)" % po2, "value": value, "unit": "cycles/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": "rv32im segment po2=%d full prove_segment (NTT + Poseidon2 Merkle + eval_check + DEEP + FRI)" % po2,
+                "config": {"workload": "rv32im segment po2=%d full prove_core from a preflight trace (witgen + accum + NTT + Poseidon2 "
+                                       "Merkle + eval_check + DEEP + FRI), loop guest" % po2,
+                           "guest": "execute/testutil.rs kernel::simple_loop, first (full) segment; real, constraint-satisfying witness",
                            "segments_per_step_per_gpu": 1, "user_cycles_per_segment": cycles, "total_cycles_per_segment": n,
-                           "hash": args.hash, "l2": "inputs (1.3 GB witness, 5.5 GB evaluations) exceed the 126 MB L2",
-                           "parallelism": "segments sharded one per GPU, no collective"},
-                "e2e": {"value": e2e_value, "unit": "cycles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(seal.nbytes),
+                           "hash": args.hash, "l2": "inputs (0.9 GB data witness, 5.5 GB evaluations) exceed the 126 MB L2",
+                           "parallelism": "segments sharded one per GPU, no collective",
+                           "setup_s": round(t_setup, 1)},
+                "e2e": {"value": e2e_value, "unit": "cycles/s", "h2d_bytes_per_step": int(pf.h2d_bytes), "d2h_bytes_per_step": int(seal.nbytes) + 360,
                         "ms_per_step": e2e_ms / args.steps,
-                        "pipeline": "depth 2 for code + data (r0b200_witness_upload of step s+1 before step s is proved); accum is "
-                                    "uploaded between r0b200_prove_begin (which draws the mix accum depends on) and "
-                                    "r0b200_prove_finish, i.e. on the critical path of every step; all K uploads and K seal "
-                                    "reads are inside the timed region"},
+                        "pipeline": "each step uploads its own segment (preflight trace + injector + globals) from pinned host memory "
+                                    "with r0b200_segment_upload on the copy stream, one step ahead of the proof (depth 2), and reads the "
+                                    "seal + globals back; the witness matrices never exist on the host"},
                 "gpu_launches": int(launches), "roofline": roofline, "int32_roofline": int32, "cpu_baseline": cpu_baseline,
                 "phase_ms_per_step": phase_ms, "phase_alg_GBps": phase_gbs, "clocks": sampler.result(),
-                "seal_words": int(len(seal)), "peak_device_bytes": hal.bytes_peak()}
+                "seal_words": int(len(seal)), "peak_device_bytes": hal.bytes_peak(), "configs": extras}
         emit(line)
     hal.close()
     if world > 1:

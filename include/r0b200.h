@@ -218,17 +218,30 @@ r0b200_err r0b200_accum_rv32im(r0b200_ctx* ctx, r0b200_trace* trace, uint32_t* d
 /* SegmentProverImpl::prove_core (rv32im/src/prove/hal/mod.rs:143-224) from a PreflightResults
  * (prove/witgen/mod.rs:55-88), everything on the device: WitnessGenerator::new (INVALID fill, injector scatter,
  * generate_witness, zeroize), commit code + data, mix draw, WitnessGenerator::accum (step_accum from that mix), commit
- * accum, finalize -> seal. Host inputs: the trace, the global vector (90 words, INVALID where the witness generator
- * fills the value) and the injector as the reference builds it (CSR: index[cycles + 1], word offsets col * cycles + row,
- * Montgomery values; witgen/mod.rs:226-270,320-370). acc_*: the BigIntAccum injector of WitnessGenerator::accum
- * (:186-207) - NOTE it depends on the mix; pass NULL / 0 for segments without bigint cycles (a segment with bigint
- * cycles must use prove_begin / accum / prove_finish). global_out_host (90 words, may be NULL) receives the globals
- * after witness generation (zeroized), i.e. the journal side of the claim. */
+ * accum, finalize -> seal.
+ *   r0b200_segment_upload : copies a segment's prover inputs to the device on the context's COPY stream and returns at
+ *                           once: the trace, the global vector (90 words, INVALID where the witness generator fills
+ *                           the value) and the injector as the reference builds it (CSR: index[cycles + 1], word
+ *                           offsets col * cycles + row, Montgomery values; witgen/mod.rs:226-270,320-370). Host
+ *                           buffers must stay valid until the segment has been proved (pinned memory makes the copies
+ *                           asynchronous). Uploading segment s + 1 before proving segment s overlaps the transfer with
+ *                           compute - the reference's CPU -> GPU queue (r0vm/src/actors/worker.rs:70-76,585).
+ *   r0b200_prove_segment  : proves an uploaded segment (it can be proved again; free it with r0b200_segment_free).
+ *                           global_out_host (90 words, may be NULL) receives the globals after witness generation.
+ *   r0b200_prove_segment_rv32im : upload + prove + free in one call.
+ * Segments with bigint cycles need the BigIntAccum injector, which depends on the mix (witgen/mod.rs:186-207): they go
+ * through r0b200_prove_begin / r0b200_accum_rv32im / r0b200_prove_finish instead. */
+typedef struct r0b200_segment r0b200_segment;
+r0b200_err r0b200_segment_upload(r0b200_ctx* ctx, uint32_t po2, const r0b200_preflight_trace* trace_host,
+                                 const uint32_t* global_host, const uint32_t* inj_index_host, size_t inj_index_len,
+                                 const uint32_t* inj_offsets_host, const uint32_t* inj_values_host, r0b200_segment** out);
+void r0b200_segment_free(r0b200_segment* segment);
+r0b200_err r0b200_prove_segment(r0b200_ctx* ctx, int hash, r0b200_segment* segment, uint32_t* seal_out_host,
+                                size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap,
+                                size_t* nroots, uint32_t* query_pos_out_host, uint32_t* global_out_host);
 r0b200_err r0b200_prove_segment_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const r0b200_preflight_trace* trace_host,
                                        const uint32_t* global_host, const uint32_t* inj_index_host, size_t inj_index_len,
                                        const uint32_t* inj_offsets_host, const uint32_t* inj_values_host,
-                                       const uint32_t* acc_index_host, size_t acc_index_len,
-                                       const uint32_t* acc_offsets_host, const uint32_t* acc_values_host,
                                        uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host,
                                        size_t roots_cap, size_t* nroots, uint32_t* query_pos_out_host,
                                        uint32_t* global_out_host);

@@ -339,10 +339,31 @@ static const char* finish(SealOut* so, uint32_t* seal_out, uint64_t seal_cap, ui
 // prove_core's prove_inner block (rv32im/src/prove/hal/mod.rs:171-222). mix_out (36 words, may be null) receives the
 // accum mix drawn after the code and data commits (:213); with accum == nullptr the function stops there - that is
 // what a caller sees between the two phases (the accum matrix is computed from that mix, :213-216).
+typedef void (*accum_cb_t)(const uint32_t* mix, uint32_t* accum_out);
+static const char* prove_rv32im_impl(int hash_kind, uint32_t po2, const uint32_t* code, const uint32_t* data,
+                                     const uint32_t* accum, const uint32_t* global, uint32_t* mix_out, uint32_t* seal_out,
+                                     uint64_t seal_cap, uint64_t* seal_len, uint32_t* roots_out, uint64_t roots_cap,
+                                     uint64_t* nroots, uint32_t* qpos_out, accum_cb_t accum_cb);
 static const char* prove_rv32im_impl(int hash_kind, uint32_t po2, const uint32_t* code, const uint32_t* data,
                                      const uint32_t* accum, const uint32_t* global, uint32_t* mix_out, uint32_t* seal_out,
                                      uint64_t seal_cap, uint64_t* seal_len, uint32_t* roots_out, uint64_t roots_cap,
                                      uint64_t* nroots, uint32_t* qpos_out) {
+  return prove_rv32im_impl(hash_kind, po2, code, data, accum, global, mix_out, seal_out, seal_cap, seal_len, roots_out,
+                           roots_cap, nroots, qpos_out, nullptr);
+}
+// two-phase form, the real protocol order (rv32im/src/prove/hal/mod.rs:209-217): the accum matrix comes from a
+// callback that receives the mix drawn after the data commit
+extern "C" const char* orc_prove_rv32im_cb(int hash_kind, uint32_t po2, const uint32_t* code, const uint32_t* data,
+                                           const uint32_t* global, accum_cb_t accum_cb, uint32_t* seal_out,
+                                           uint64_t seal_cap, uint64_t* seal_len, uint32_t* roots_out, uint64_t roots_cap,
+                                           uint64_t* nroots, uint32_t* qpos_out) {
+  return prove_rv32im_impl(hash_kind, po2, code, data, nullptr, global, nullptr, seal_out, seal_cap, seal_len, roots_out,
+                           roots_cap, nroots, qpos_out, accum_cb);
+}
+static const char* prove_rv32im_impl(int hash_kind, uint32_t po2, const uint32_t* code, const uint32_t* data,
+                                     const uint32_t* accum, const uint32_t* global, uint32_t* mix_out, uint32_t* seal_out,
+                                     uint64_t seal_cap, uint64_t* seal_len, uint32_t* roots_out, uint64_t roots_cap,
+                                     uint64_t* nroots, uint32_t* qpos_out, accum_cb_t accum_cb) {
   ORC_TRY
   HashSuite suite = suite_of(hash_kind);
   TapSet taps = rv32im_taps();
@@ -372,6 +393,14 @@ static const char* prove_rv32im_impl(int hash_kind, uint32_t po2, const uint32_t
   for (auto& m : mix) m = prover.iop.random_elem();
   if (mix_out)
     for (size_t i = 0; i < RV32IM_MIX_SIZE; i++) mix_out[i] = mix[i].v;
+  std::vector<uint32_t> accum_from_cb;
+  if (!accum && accum_cb) {
+    accum_from_cb.resize(N * 103);
+    std::vector<uint32_t> mix_words(RV32IM_MIX_SIZE);
+    for (size_t i = 0; i < RV32IM_MIX_SIZE; i++) mix_words[i] = mix[i].v;
+    accum_cb(mix_words.data(), accum_from_cb.data());
+    accum = accum_from_cb.data();
+  }
   if (!accum) return nullptr;
   prover.commit_group(0, (const Fp*)accum, N * 103);
   EvalCheckFn ec = [&](Fp* check, const std::vector<const Fp*>& g, const std::vector<const Fp*>& globals, FpExt pm,

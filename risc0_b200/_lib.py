@@ -51,6 +51,8 @@ def load_library():
         _lib.r0b200_free_error.restype = None
         _lib.r0b200_witness_free.restype = None
         _lib.r0b200_prove_abort.restype = None
+        _lib.r0b200_trace_free.restype = None
+        _lib.r0b200_segment_free.restype = None
         _lib.r0b200_launch_count.restype = C.c_uint64
         _lib.r0b200_bytes_peak.restype = C.c_uint64
         _lib.r0b200_stream.restype = C.c_void_p

@@ -71,7 +71,7 @@ void r0_eval_check_recursion(r0::Ctx* c, uint32_t* check, const uint32_t* accum,
                              const r0::FpExt& poly_mix, uint32_t po2);
 
 // rv32im witness generation / accumulation on the device (witgen.cu)
-r0b200_trace* r0_trace_upload(r0::Ctx* c, const r0b200_preflight_trace* trace_host, uint32_t cycles);
+r0b200_trace* r0_trace_upload(r0::Ctx* c, const r0b200_preflight_trace* trace_host, uint32_t cycles, cudaStream_t stream);
 void r0_trace_free(r0b200_trace* t);
 void r0_witgen_rv32im(r0::Ctx* c, r0b200_trace* t, uint32_t* global, uint32_t* data, bool sync_check);
 void r0_accum_rv32im(r0::Ctx* c, r0b200_trace* t, uint32_t* data, uint32_t* accum, uint32_t* global, uint32_t* mix,

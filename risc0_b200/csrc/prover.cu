@@ -684,41 +684,88 @@ extern "C" void r0b200_prove_abort(r0b200_proof* proof) {
   delete proof;
 }
 
+// A segment's prover inputs resident on the device: the preflight trace (sorted), the injector CSR and the globals -
+// what PreflightResults carries (prove/witgen/mod.rs:55-61). Uploaded on the copy stream so that segment s + 1 travels
+// while segment s is proved (the reference's CPU -> GPU queue of depth 2, r0vm/src/actors/worker.rs:70-76,585).
+struct r0b200_segment {
+  r0b200_ctx* ctx = nullptr;
+  uint32_t po2 = 0;
+  r0b200_trace* trace = nullptr;
+  uint32_t *d_index = nullptr, *d_offsets = nullptr, *d_values = nullptr;
+  size_t index_len = 0, nvals = 0;
+  std::vector<uint32_t> global;
+  cudaEvent_t ready = nullptr;
+};
+
+extern "C" void r0b200_segment_free(r0b200_segment* seg) {
+  if (!seg) return;
+  cudaSetDevice(seg->ctx->device);
+  if (seg->ready) cudaEventDestroy(seg->ready);
+  r0_trace_free(seg->trace);
+  for (uint32_t* p : {seg->d_index, seg->d_offsets, seg->d_values})
+    if (p) cudaFreeAsync(p, seg->ctx->stream);
+  delete seg;
+}
+
+extern "C" r0b200_err r0b200_segment_upload(r0b200_ctx* ctx, uint32_t po2, const r0b200_preflight_trace* trace_host,
+                                            const uint32_t* global_host, const uint32_t* inj_index_host,
+                                            size_t inj_index_len, const uint32_t* inj_offsets_host,
+                                            const uint32_t* inj_values_host, r0b200_segment** out) {
+  R0_API_BEGIN
+  R0_CHECK(ctx != nullptr && trace_host != nullptr && global_host != nullptr && out != nullptr, "segment_upload: null argument");
+  R0_CHECK(po2 >= 9 && po2 + 2 <= (uint32_t)MAX_LG, "segment_upload: po2 out of range (9..22)");
+  R0_CUDA(cudaSetDevice(ctx->device));
+  const size_t cycles = size_t(1) << po2;
+  R0_CHECK(inj_index_len == 0 || inj_index_len == cycles + 1, "segment_upload: injector index must have cycles + 1 entries");
+  struct Guard {
+    r0b200_segment* s;
+    ~Guard() { r0b200_segment_free(s); }
+  } g{new r0b200_segment()};
+  r0b200_segment* seg = g.s;
+  seg->ctx = ctx;
+  seg->po2 = po2;
+  seg->global.assign(global_host, global_host + kRv32im.output_size);
+  cudaStream_t cs = ctx->copy_stream;
+  seg->trace = r0_trace_upload(ctx, trace_host, (uint32_t)cycles, cs);
+  if (inj_index_len >= 2) {
+    seg->index_len = inj_index_len;
+    seg->nvals = inj_index_host[inj_index_len - 1];
+    R0_CUDA(cudaMallocAsync(&seg->d_index, inj_index_len * 4, cs));
+    R0_CUDA(cudaMallocAsync(&seg->d_offsets, std::max<size_t>(1, seg->nvals) * 4, cs));
+    R0_CUDA(cudaMallocAsync(&seg->d_values, std::max<size_t>(1, seg->nvals) * 4, cs));
+    R0_CUDA(cudaMemcpyAsync(seg->d_index, inj_index_host, inj_index_len * 4, cudaMemcpyHostToDevice, cs));
+    R0_CUDA(cudaMemcpyAsync(seg->d_offsets, inj_offsets_host, seg->nvals * 4, cudaMemcpyHostToDevice, cs));
+    R0_CUDA(cudaMemcpyAsync(seg->d_values, inj_values_host, seg->nvals * 4, cudaMemcpyHostToDevice, cs));
+  }
+  R0_CUDA(cudaEventCreateWithFlags(&seg->ready, cudaEventDisableTiming));
+  R0_CUDA(cudaEventRecord(seg->ready, cs));
+  g.s = nullptr;
+  *out = seg;
+  R0_API_END
+}
+
 // prove_core from a PreflightResults (rv32im/src/prove/hal/mod.rs:143-224): WitnessGenerator::new on the device
 // (prove/witgen/mod.rs:130-176: INVALID fill, injector scatter, generate_witness, zeroize), the two group commits, the
 // mix draw, WitnessGenerator::accum (:178-224: step_accum from that mix, zeroize), the accum commit and finalize.
-extern "C" r0b200_err r0b200_prove_segment_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2,
-                                                  const r0b200_preflight_trace* trace_host, const uint32_t* global_host,
-                                                  const uint32_t* inj_index_host, size_t inj_index_len,
-                                                  const uint32_t* inj_offsets_host, const uint32_t* inj_values_host,
-                                                  const uint32_t* acc_index_host, size_t acc_index_len,
-                                                  const uint32_t* acc_offsets_host, const uint32_t* acc_values_host,
-                                                  uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len,
-                                                  uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
-                                                  uint32_t* query_pos_out_host, uint32_t* global_out_host) {
-  R0_API_BEGIN
-  R0_CHECK(ctx != nullptr && trace_host != nullptr && global_host != nullptr, "prove_segment: null argument");
-  R0_CHECK(po2 >= 9 && po2 + 2 <= (uint32_t)MAX_LG, "prove_segment: po2 out of range (9..22)");
-  R0_CUDA(cudaSetDevice(ctx->device));
+static void prove_core_rv32im(r0b200_ctx* ctx, int hash, r0b200_segment* seg, uint32_t* seal_out_host, size_t seal_cap,
+                              size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
+                              uint32_t* query_pos_out_host, uint32_t* global_out_host) {
   NvtxRange range("prove_core");
+  const uint32_t po2 = seg->po2;
   const size_t cycles = size_t(1) << po2;
   const CircuitDesc& d = kRv32im;
-  struct TraceGuard {
-    r0b200_trace* t;
-    ~TraceGuard() { r0_trace_free(t); }
-  } trace{nullptr};
+  R0_CUDA(cudaStreamWaitEvent(ctx->stream, seg->ready, 0));
   DevBuf data, code, accum, d_global(ctx, d.output_size), d_mix(ctx, d.mix_size);
   std::vector<uint32_t> global(d.output_size);
   {
     NvtxRange r2("witness_generator_new");
-    trace.t = r0_trace_upload(ctx, trace_host, (uint32_t)cycles);
     data = DevBuf(ctx, d.group_sizes[2] * cycles);
     r0_fill(ctx, data.p, FP_INVALID, data.words);
-    if (inj_index_len >= 2) r0_scatter(ctx, data.p, inj_index_host, inj_index_len, inj_offsets_host, inj_values_host);
-    R0_CUDA(cudaMemcpyAsync(d_global.p, global_host, d.output_size * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (seg->index_len >= 2) r0_scatter_dev(ctx, data.p, seg->d_index, seg->index_len - 1, seg->d_offsets, seg->d_values);
+    R0_CUDA(cudaMemcpyAsync(d_global.p, seg->global.data(), d.output_size * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
       NvtxRange r3("witgen");
-      r0_witgen_rv32im(ctx, trace.t, d_global.p, data.p, /*sync_check=*/true);
+      r0_witgen_rv32im(ctx, seg->trace, d_global.p, data.p, /*sync_check=*/true);
     }
     NvtxRange r4("zeroize");
     r0_eltwise_zeroize(ctx, d_global.p, d.output_size);
@@ -734,14 +781,40 @@ extern "C" r0b200_err r0b200_prove_segment_rv32im(r0b200_ctx* ctx, int hash, uin
     NvtxRange r2("accumulate");
     accum = DevBuf(ctx, d.group_sizes[0] * cycles);
     r0_fill(ctx, accum.p, FP_INVALID, accum.words);
-    if (acc_index_len >= 2) r0_scatter(ctx, accum.p, acc_index_host, acc_index_len, acc_offsets_host, acc_values_host);
     R0_CUDA(cudaMemcpyAsync(d_mix.p, p->mix.data(), d.mix_size * 4, cudaMemcpyHostToDevice, ctx->stream));
-    r0_accum_rv32im(ctx, trace.t, data.p, accum.p, d_global.p, d_mix.p, /*sync_check=*/true);
+    r0_accum_rv32im(ctx, seg->trace, data.p, accum.p, d_global.p, d_mix.p, /*sync_check=*/true);
     r0_eltwise_zeroize(ctx, accum.p, accum.words);
   }
   proof_finish(p.get(), accum.p, 0, seal_out_host, seal_cap, seal_len, roots_out_host, roots_cap, nroots,
                query_pos_out_host);
+}
+
+extern "C" r0b200_err r0b200_prove_segment(r0b200_ctx* ctx, int hash, r0b200_segment* segment, uint32_t* seal_out_host,
+                                           size_t seal_cap, size_t* seal_len, uint32_t* roots_out_host, size_t roots_cap,
+                                           size_t* nroots, uint32_t* query_pos_out_host, uint32_t* global_out_host) {
+  R0_API_BEGIN
+  R0_CHECK(ctx != nullptr && segment != nullptr && segment->ctx == ctx, "prove_segment: segment belongs to another context");
+  R0_CUDA(cudaSetDevice(ctx->device));
+  prove_core_rv32im(ctx, hash, segment, seal_out_host, seal_cap, seal_len, roots_out_host, roots_cap, nroots,
+                    query_pos_out_host, global_out_host);
   R0_API_END
+}
+
+extern "C" r0b200_err r0b200_prove_segment_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2,
+                                                  const r0b200_preflight_trace* trace_host, const uint32_t* global_host,
+                                                  const uint32_t* inj_index_host, size_t inj_index_len,
+                                                  const uint32_t* inj_offsets_host, const uint32_t* inj_values_host,
+                                                  uint32_t* seal_out_host, size_t seal_cap, size_t* seal_len,
+                                                  uint32_t* roots_out_host, size_t roots_cap, size_t* nroots,
+                                                  uint32_t* query_pos_out_host, uint32_t* global_out_host) {
+  r0b200_segment* seg = nullptr;
+  r0b200_err e = r0b200_segment_upload(ctx, po2, trace_host, global_host, inj_index_host, inj_index_len, inj_offsets_host,
+                                       inj_values_host, &seg);
+  if (e) return e;
+  e = r0b200_prove_segment(ctx, hash, seg, seal_out_host, seal_cap, seal_len, roots_out_host, roots_cap, nroots,
+                           query_pos_out_host, global_out_host);
+  r0b200_segment_free(seg);
+  return e;
 }
 
 extern "C" r0b200_err r0b200_prove_rv32im(r0b200_ctx* ctx, int hash, uint32_t po2, const uint32_t* code,

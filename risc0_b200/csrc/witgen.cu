@@ -200,13 +200,14 @@ const char* kErrNames[] = {"", "Inconsistent set", "Read of unset value", "eqz f
                            "memory peek not in preflight", "Invalid lookup table", "u8/16 table error",
                            "Reached unreachable mux arm"};
 
-void sort_range(Ctx* c, r0b200_trace* t, uint32_t begin, uint32_t count, uint32_t* order, uint32_t* scratch_hist) {
+void sort_range(Ctx* c, cudaStream_t stream, r0b200_trace* t, uint32_t begin, uint32_t count, uint32_t* order,
+                uint32_t* scratch_hist) {
   if (count == 0) return;
-  R0_CUDA(cudaMemsetAsync(scratch_hist, 0, NKEYS * 4, c->stream));
+  R0_CUDA(cudaMemsetAsync(scratch_hist, 0, NKEYS * 4, stream));
   const unsigned blocks = (unsigned)std::min<size_t>((count + 1023) / 1024, (size_t)c->sm_count * 4);
-  k_key_histogram<<<blocks, 256, 0, c->stream>>>(t->d_cycles, begin, count, scratch_hist);
-  k_key_offsets<<<1, 32, 0, c->stream>>>(scratch_hist);
-  k_key_scatter<<<blocks, 256, 0, c->stream>>>(t->d_cycles, begin, count, scratch_hist, order);
+  k_key_histogram<<<blocks, 256, 0, stream>>>(t->d_cycles, begin, count, scratch_hist);
+  k_key_offsets<<<1, 32, 0, stream>>>(scratch_hist);
+  k_key_scatter<<<blocks, 256, 0, stream>>>(t->d_cycles, begin, count, scratch_hist, order);
   count_launch(c, 3);
   R0_CUDA(cudaGetLastError());
 }
@@ -246,7 +247,9 @@ void upload_shared(Ctx* c, r0b200_trace* t, uint32_t* data, uint32_t* accum, uin
 
 }  // namespace
 
-r0b200_trace* r0_trace_upload(Ctx* c, const r0b200_preflight_trace* h, uint32_t cycles) {
+// `stream`: the stream the allocations, copies and the sort run on (the compute stream, or the copy stream when a
+// segment is uploaded while the previous one is being proved); the trace is released on the compute stream
+r0b200_trace* r0_trace_upload(Ctx* c, const r0b200_preflight_trace* h, uint32_t cycles, cudaStream_t stream) {
   R0_CHECK(h != nullptr && h->cycles != nullptr && (h->txns != nullptr || h->txns_len == 0), "trace_upload: null trace");
   R0_CHECK(cycles > 0 && (cycles & (cycles - 1)) == 0, "trace_upload: cycle count must be a power of two");
   R0_CHECK(h->table_split_cycle <= cycles, "trace_upload: table split beyond the last cycle");
@@ -256,7 +259,7 @@ r0b200_trace* r0_trace_upload(Ctx* c, const r0b200_preflight_trace* h, uint32_t 
   t->txns_len = h->txns_len;
   t->bigint_len = h->bigint_bytes_len;
   t->split = h->table_split_cycle;
-  cudaStream_t s = c->stream;
+  cudaStream_t s = stream ? stream : c->stream;
   R0_CUDA(cudaMallocAsync(&t->d_cycles, (size_t)cycles * sizeof(PreflightCycle), s));
   R0_CUDA(cudaMallocAsync(&t->d_txns, std::max<size_t>(1, h->txns_len) * sizeof(MemoryTxn), s));
   R0_CUDA(cudaMallocAsync(&t->d_bigint, std::max<size_t>(16, h->bigint_bytes_len), s));
@@ -273,9 +276,9 @@ r0b200_trace* r0_trace_upload(Ctx* c, const r0b200_preflight_trace* h, uint32_t 
     R0_CUDA(cudaMemcpyAsync(t->d_bigint, h->bigint_bytes, h->bigint_bytes_len, cudaMemcpyHostToDevice, s));
   R0_CUDA(cudaMemcpyAsync(t->d_layout, kLayoutHost, sizeof(kLayoutHost), cudaMemcpyHostToDevice, s));
   uint32_t* hist = t->d_tables + 256 + 65536;
-  sort_range(c, t.get(), 0, t->split, t->d_order, hist);
-  sort_range(c, t.get(), t->split, cycles - t->split, t->d_order, hist);
-  sort_range(c, t.get(), 0, cycles, t->d_order_all, hist);
+  sort_range(c, s, t.get(), 0, t->split, t->d_order, hist);
+  sort_range(c, s, t.get(), t->split, cycles - t->split, t->d_order, hist);
+  sort_range(c, s, t.get(), 0, cycles, t->d_order_all, hist);
   return t.release();
 }
 
@@ -330,7 +333,7 @@ r0b200_err r0b200_trace_upload(r0b200_ctx* ctx, const r0b200_preflight_trace* tr
   R0_API_BEGIN
   R0_CHECK(ctx != nullptr && out != nullptr, "trace_upload: null argument");
   R0_CUDA(cudaSetDevice(ctx->device));
-  *out = r0_trace_upload(ctx, trace_host, cycles);
+  *out = r0_trace_upload(ctx, trace_host, cycles, ctx->stream);
   R0_API_END
 }
 void r0b200_trace_free(r0b200_trace* trace) {

@@ -494,6 +494,37 @@ class SegmentProver:
     def abort(self, proof):
         self.hal._l.r0b200_prove_abort(proof)
 
+    def upload_segment(self, pf):
+        """r0b200_segment_upload: enqueue the copy of a PreflightResults (trace, injector, globals) on the copy stream.
+        Returns a handle for prove_segment(); call it for segment s + 1 before proving segment s."""
+        hal = self.hal
+        st, keep = _trace_struct(pf)
+        index, offsets, values = (_u32(a) for a in pf.injector)
+        glob = _u32(pf.global_)
+        h = C.c_void_p()
+        check(hal._l.r0b200_segment_upload(hal._ctx, C.c_uint32(pf.po2), C.byref(st), _np_ptr(glob), _np_ptr(index),
+                                           C.c_size_t(index.size), _np_ptr(offsets), _np_ptr(values), C.byref(h)))
+        return (h, (keep, index, offsets, values, glob))
+
+    def prove_segment(self, segment, free=True):
+        """prove_core on an uploaded segment -> (seal, roots, query positions, globals)"""
+        hal = self.hal
+        h, _keep = segment
+        glob_out = np.zeros(90, dtype=np.uint32)
+        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
+        try:
+            check(hal._l.r0b200_prove_segment(hal._ctx, hal.hash, h, _np_ptr(self._seal), C.c_size_t(self.seal_cap),
+                                              C.byref(seal_len), _np_ptr(self._roots), C.c_size_t(16), C.byref(nroots),
+                                              _np_ptr(self._qpos), _np_ptr(glob_out)))
+        finally:
+            if free:
+                hal._l.r0b200_segment_free(h)
+        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
+                self._qpos.copy(), glob_out)
+
+    def free_segment(self, segment):
+        self.hal._l.r0b200_segment_free(segment[0])
+
     def prove_core(self, pf):
         """SegmentProverImpl::prove_core (rv32im/src/prove/hal/mod.rs:143-224) from a PreflightResults, everything on
         the device in one call (r0b200_prove_segment_rv32im). Returns (seal, roots, query positions, globals)."""
@@ -505,47 +536,7 @@ class SegmentProver:
         seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
         check(hal._l.r0b200_prove_segment_rv32im(
             hal._ctx, hal.hash, C.c_uint32(pf.po2), C.byref(st), _np_ptr(glob), _np_ptr(index), C.c_size_t(index.size),
-            _np_ptr(offsets), _np_ptr(values), None, C.c_size_t(0), None, None, _np_ptr(self._seal),
-            C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots), C.c_size_t(16), C.byref(nroots),
-            _np_ptr(self._qpos), _np_ptr(glob_out)))
+            _np_ptr(offsets), _np_ptr(values), _np_ptr(self._seal), C.c_size_t(self.seal_cap), C.byref(seal_len),
+            _np_ptr(self._roots), C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos), _np_ptr(glob_out)))
         return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
                 self._qpos.copy(), glob_out)
-
-    def prove_uploaded(self, uploaded, glob):
-        hal = self.hal
-        h, _keep = uploaded
-        glob = _u32(glob)
-        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
-        try:
-            check(hal._l.r0b200_prove_uploaded(hal._ctx, hal.hash, h, _np_ptr(glob), _np_ptr(self._seal),
-                                               C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots),
-                                               C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
-        finally:
-            hal._l.r0b200_witness_free(h)
-        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
-                self._qpos.copy())
-
-    def prove(self, po2, code, data, accum, glob, circuit="rv32im"):
-        """returns (seal words, committed roots [k, 8], drawn query positions [50]). circuit = "rv32im"
-        (prove_core, rv32im/src/prove/hal/mod.rs:171-222) or "recursion" (recursion/src/prove/mod.rs:179-224)"""
-        hal = self.hal
-        on_host = isinstance(data, np.ndarray)
-        n = 1 << po2
-        c_code, c_data, c_accum, n_glob = self.SHAPES[circuit]
-        if on_host:
-            code, data, accum = _u32(code), _u32(data), _u32(accum)
-            assert code.size == c_code * n and data.size == c_data * n and accum.size == c_accum * n
-            ptrs = [_np_ptr(code), _np_ptr(data), _np_ptr(accum)]
-        else:
-            assert code.size() == c_code * n and data.size() == c_data * n and accum.size() == c_accum * n
-            ptrs = [code.ptr, data.ptr, accum.ptr]
-        glob = _u32(glob)
-        assert glob.size == n_glob
-        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
-        fn = hal._l.r0b200_prove_rv32im if circuit == "rv32im" else hal._l.r0b200_prove_recursion
-        check(fn(hal._ctx, hal.hash, C.c_uint32(po2), ptrs[0], ptrs[1], ptrs[2],
-                 C.c_int(1 if on_host else 0), _np_ptr(glob), _np_ptr(self._seal),
-                 C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots),
-                 C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
-        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
-                self._qpos.copy())

@@ -361,6 +361,29 @@ def prove_rv32im_mix(po2, code, data, glob, kind=POSEIDON2):
     return mix
 
 
+def prove_rv32im_two_phase(po2, code, data, glob, accum_fn, kind=POSEIDON2):
+    """CPU prove_core in the protocol order: accum_fn(mix) -> accum matrix is called after code and data have been
+    committed and the mix drawn (rv32im/src/prove/hal/mod.rs:209-217). Returns (seal, roots, query positions)."""
+    load_ref()
+    n = 1 << po2
+    u32p = C.POINTER(C.c_uint32)
+    proto = C.CFUNCTYPE(None, u32p, u32p)
+
+    def cb(mix_ptr, accum_ptr):
+        mix = np.ctypeslib.as_array(mix_ptr, shape=(36,)).copy()
+        out = np.ctypeslib.as_array(accum_ptr, shape=(103 * n,))
+        out[:] = u32(accum_fn(mix))
+
+    seal = np.zeros(1 << 20, dtype=np.uint32)
+    roots = np.zeros(8 * 16, dtype=np.uint32)
+    qpos = np.zeros(50, dtype=np.uint32)
+    n_, nr = _u64(0), _u64(0)
+    keep = proto(cb)
+    _check(lib().orc_prove_rv32im_cb(C.c_int(kind), C.c_uint32(po2), ptr(u32(code)), ptr(u32(data)), ptr(u32(glob)), keep,
+                                     ptr(seal), _u64(seal.size), C.byref(n_), ptr(roots), _u64(16), C.byref(nr), ptr(qpos)))
+    return seal[:n_.value].copy(), roots[:8 * nr.value].reshape(-1, 8).copy(), qpos
+
+
 def prove_hello(po2, accum, code, data, kind=POSEIDON2):
     cap = 1 << 20
     seal = np.zeros(cap, dtype=np.uint32)

@@ -110,3 +110,17 @@ def test_verifier_rejects_a_witness_that_violates_constraints(hal):
     with pytest.raises(Exception) as ei:
         O.verify_with_validity(seal)
     assert "constraint" in str(ei.value)
+
+
+def test_segment_upload_pipeline(hal):
+    # r0b200_segment_upload / r0b200_prove_segment: two segments in flight (the upload of the second overlaps the proof
+    # of the first), an uploaded segment can be proved twice, and the seals equal the one-call form's
+    pfs = [PF.PreflightResults(seg(n), (41, 42, 43, 44)) for n in ("loop_po2_13", "all_insn")]
+    prover = SegmentProver(hal)
+    want = [prover.prove_core(pf)[0] for pf in pfs]
+    s0 = prover.upload_segment(pfs[0])
+    s1 = prover.upload_segment(pfs[1])
+    got0 = prover.prove_segment(s0, free=False)[0]
+    got1 = prover.prove_segment(s1)[0]
+    again = prover.prove_segment(s0)[0]
+    assert np.array_equal(got0, want[0]) and np.array_equal(got1, want[1]) and np.array_equal(again, want[0])
