@@ -540,3 +540,42 @@ class SegmentProver:
             _np_ptr(self._roots), C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos), _np_ptr(glob_out)))
         return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
                 self._qpos.copy(), glob_out)
+
+    def prove_uploaded(self, uploaded, glob):
+        hal = self.hal
+        h, _keep = uploaded
+        glob = _u32(glob)
+        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
+        try:
+            check(hal._l.r0b200_prove_uploaded(hal._ctx, hal.hash, h, _np_ptr(glob), _np_ptr(self._seal),
+                                               C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots),
+                                               C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
+        finally:
+            hal._l.r0b200_witness_free(h)
+        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
+                self._qpos.copy())
+
+    def prove(self, po2, code, data, accum, glob, circuit="rv32im"):
+        """returns (seal words, committed roots [k, 8], drawn query positions [50]). circuit = "rv32im"
+        (prove_core, rv32im/src/prove/hal/mod.rs:171-222) or "recursion" (recursion/src/prove/mod.rs:179-224)"""
+        hal = self.hal
+        on_host = isinstance(data, np.ndarray)
+        n = 1 << po2
+        c_code, c_data, c_accum, n_glob = self.SHAPES[circuit]
+        if on_host:
+            code, data, accum = _u32(code), _u32(data), _u32(accum)
+            assert code.size == c_code * n and data.size == c_data * n and accum.size == c_accum * n
+            ptrs = [_np_ptr(code), _np_ptr(data), _np_ptr(accum)]
+        else:
+            assert code.size() == c_code * n and data.size() == c_data * n and accum.size() == c_accum * n
+            ptrs = [code.ptr, data.ptr, accum.ptr]
+        glob = _u32(glob)
+        assert glob.size == n_glob
+        seal_len, nroots = C.c_size_t(0), C.c_size_t(0)
+        fn = hal._l.r0b200_prove_rv32im if circuit == "rv32im" else hal._l.r0b200_prove_recursion
+        check(fn(hal._ctx, hal.hash, C.c_uint32(po2), ptrs[0], ptrs[1], ptrs[2],
+                 C.c_int(1 if on_host else 0), _np_ptr(glob), _np_ptr(self._seal),
+                 C.c_size_t(self.seal_cap), C.byref(seal_len), _np_ptr(self._roots),
+                 C.c_size_t(16), C.byref(nroots), _np_ptr(self._qpos)))
+        return (self._seal[:seal_len.value].copy(), self._roots[:8 * nroots.value].reshape(-1, 8).copy(),
+                self._qpos.copy())

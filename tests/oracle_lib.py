@@ -28,7 +28,9 @@ def build(force=False):
     srcs += [os.path.join(ORACLE_DIR, "tables", f) for f in os.listdir(os.path.join(ORACLE_DIR, "tables"))]
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
-    if not (os.path.exists(REF_LIB) and os.path.exists(REF_LIB_RECURSION)) and os.path.isdir("/root/reference"):
+    ref_witgen = os.path.join(ORACLE_DIR, "_ref", "librv32im_witgen_ref.so")
+    if not (os.path.exists(REF_LIB) and os.path.exists(REF_LIB_RECURSION) and os.path.exists(ref_witgen)) and \
+            os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-j5", "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -43,7 +45,8 @@ def lib():
         for name in ("orc_load_ref", "orc_batch_expand_into_evaluate_ntt", "orc_hash_fold", "orc_combos_divide",
                      "orc_prove_rv32im", "orc_prove_hello", "orc_verify_hello", "orc_verify_rv32im",
                      "orc_rv32im_eval_check", "orc_load_ref_recursion", "orc_recursion_eval_check",
-                     "orc_prove_recursion", "orc_verify_recursion"):
+                     "orc_prove_recursion", "orc_verify_recursion", "orc_prove_rv32im_mix", "orc_prove_rv32im_cb",
+                     "orc_verify_rv32im_ext", "orc_verify_recursion_ext", "orc_rv32im_check_constraints"):
             getattr(_lib, name).restype = C.c_void_p
         for name in ("orc_fp_encode", "orc_fp_decode", "orc_fp_add", "orc_fp_sub", "orc_fp_mul", "orc_fp_pow",
                      "orc_fp_inv", "orc_rou_fwd", "orc_rou_rev", "orc_rng_elem", "orc_rng_bits"):
