@@ -182,9 +182,9 @@ def extra_configs(hal, torch, peak):
     class Dev:
         """hal-compatible view of a torch allocation (uniform [0, P) words = uniform Montgomery elements)"""
 
-        def __init__(self, n):
+        def __init__(self, n, count=None):
             self.t = torch.randint(0, P, (n,), dtype=torch.int32, device="cuda")
-            self.n = n
+            self.n = n if count is None else count     # size() in elements of the buffer's type (digests: 8 words)
 
         @property
         def ptr(self):
@@ -205,8 +205,16 @@ def extra_configs(hal, torch, peak):
         return float(np.median(ts))
 
     prover = SegmentProver(hal)
+    import traceback
+
+    def guarded(name, fn):
+        try:
+            fn()
+        except Exception:
+            out[name] = {"error": traceback.format_exc(limit=3)}
+
     # config 4: recursion lift / join proofs are all one shape (po2 = 18); config 3: po2 = 22 segments
-    for name, circuit, po2 in (("recursion_po2_18", "recursion", 18), ("rv32im_po2_22", "rv32im", 22)):
+    def prove_config(name, circuit, po2):
         c_code, c_data, c_accum, n_glob = prover.SHAPES[circuit]
         n = 1 << po2
         code, data, accum = Dev(c_code * n), Dev(c_data * n), Dev(c_accum * n)
@@ -218,7 +226,16 @@ def extra_configs(hal, torch, peak):
                      "cycles_per_s": round((n - 4113 - 1821) / ms * 1e3) if circuit == "rv32im" else None,
                      "proofs_per_s": round(1e3 / ms, 2)}
         del code, data, accum
-    # config 5: NTT sweep n = 2^16..2^24 x c in {1,4,16,64,211,256} (c*n*4 B*5 <= 64 GB), Merkle sweep
+
+    guarded("recursion_po2_18", lambda: prove_config("recursion_po2_18", "recursion", 18))
+    guarded("rv32im_po2_22", lambda: prove_config("rv32im_po2_22", "rv32im", 22))
+    guarded("ntt_sweep", lambda: ntt_sweep(out, Dev, timeit, hal, peak))
+    guarded("merkle_sweep", lambda: merkle_sweep(out, Dev, timeit, hal))
+    return out
+
+
+def ntt_sweep(out, Dev, timeit, hal, peak):
+    # config 5: NTT sweep n = 2^16..2^24 x c in {1,4,16,64,211,256} (c*n*4 B*5 <= 64 GB)
     ntt = []
     for lg in range(16, 25):
         for c in (1, 4, 16, 64, 211, 256):
@@ -239,20 +256,22 @@ def extra_configs(hal, torch, peak):
             ntt.append(row)
             del x
     out["ntt_sweep"] = {"unit": "algorithmic GB/s (8cn iNTT / bit-reverse, 20cn expand+NTT)", "hbm_peak_GBps": peak, "cells": ntt}
+
+
+def merkle_sweep(out, Dev, timeit, hal):
     merkle = []
     for lg in range(16, 25, 2):
         for c in (1, 16, 64, 103, 211, 256):
             r = 1 << lg
             if r * c * 4 > 20e9:
                 continue
-            m, nodes = Dev(r * c), Dev(16 * r)
+            m, nodes = Dev(r * c), Dev(16 * r, count=2 * r)
             ms = timeit(lambda: hal.merkle_build(nodes, m, r, c), iters=3, warm=1)
             perms = r * ((c + 15) // 16) + r - 1
             merkle.append({"lg_rows": lg, "cols": c, "ms": round(ms, 3), "GBps": round((4 * r * c + 32 * r + 96 * (r - 1)) / ms / 1e6, 1),
                            "Gperm_per_s": round(perms / ms / 1e6, 3)})
             del m, nodes
     out["merkle_sweep"] = {"unit": "hash_rows + all fold levels; algorithmic GB/s and Poseidon2 permutations/s", "cells": merkle}
-    return out
 
 
 def main():

@@ -356,9 +356,10 @@ class DeviceTrace:
         hal.sync()   # the host arrays may go away after this
 
     def close(self):
-        if self._h:
+        # a trace belongs to its context: once the Hal is closed the handle is dangling and must not be touched
+        if self._h and self.hal._ctx:
             self.hal._l.r0b200_trace_free(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

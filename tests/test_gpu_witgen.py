@@ -61,8 +61,8 @@ def test_device_witgen_reports_bad_traces(hal):
     with pytest.raises(Exception) as ei:
         WitnessGenerator(hal, bad)
     assert "witgen" in str(ei.value)
-    with pytest.raises(Exception):                   # the reference throws on the same trace
-        W.ref_generate_witness(bad)
+    # (the reference's witgen throws "memory peek not in preflight" for this trace too, but from inside its thread
+    # pool, which takes the process down - so it is not called here)
     WitnessGenerator(hal, pf)                        # the context is still usable afterwards
 
 
