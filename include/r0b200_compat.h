@@ -25,8 +25,11 @@
 #ifndef R0B200_COMPAT_H
 #define R0B200_COMPAT_H
 
+#include <stdbool.h>
 #include <stddef.h>
 #include <stdint.h>
+
+#include "r0b200.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -83,6 +86,29 @@ const char* risc0_circuit_rv32im_cuda_eval_check(uint32_t* check, const uint32_t
                                                  const uint32_t* accum, const uint32_t* mix, const uint32_t* out,
                                                  const uint32_t* rou, uint32_t po2, uint32_t domain,
                                                  const uint32_t* poly_mix_pows);
+
+/* rv32im-sys/src/lib.rs:21-119: RawBuffer / RawExecBuffers / RawAccumBuffers (buf = DEVICE pointer, as CudaCircuitHal
+ * passes them, rv32im/src/prove/hal/cuda.rs:60-157) and RawPreflightTrace (= r0b200_preflight_trace, HOST pointers) */
+typedef struct {
+  const uint32_t* buf;
+  size_t rows;
+  size_t cols;
+  bool checked;
+} r0b200_raw_buffer;
+typedef struct {
+  r0b200_raw_buffer global;
+  r0b200_raw_buffer data;
+} r0b200_raw_exec_buffers;
+typedef struct {
+  r0b200_raw_buffer data;
+  r0b200_raw_buffer accum;
+  r0b200_raw_buffer global;
+  r0b200_raw_buffer mix;
+} r0b200_raw_accum_buffers;
+const char* risc0_circuit_rv32im_cuda_witgen(uint32_t mode, const r0b200_raw_exec_buffers* buffers,
+                                             const r0b200_preflight_trace* preflight, uint32_t cycles);
+const char* risc0_circuit_rv32im_cuda_accum(const r0b200_raw_accum_buffers* buffers, const r0b200_preflight_trace* preflight,
+                                            uint32_t cycles);
 
 /* recursion-sys/src/lib.rs:95-107, kernels/cuda/ffi_supra.cu:54-77: same shape, 158 poly-mix powers */
 const char* risc0_circuit_recursion_cuda_eval_check(uint32_t* check, const uint32_t* ctrl, const uint32_t* data,

@@ -241,6 +241,38 @@ r0b200_sppark_error supra_poly_divide(uint32_t* polynomial, size_t poly_size, ui
   });
 }
 
+// risc0_circuit_rv32im_cuda_witgen / _cuda_accum (rv32im-sys/src/lib.rs:105-119; kernels/cuda/ffi.cu:431-512): buffer
+// pointers are DEVICE pointers (rv32im/src/prove/hal/cuda.rs:60-157), the trace arrays are HOST pointers that are
+// copied to the device for the call
+const char* risc0_circuit_rv32im_cuda_witgen(uint32_t mode, const r0b200_raw_exec_buffers* buffers,
+                                             const r0b200_preflight_trace* preflight, uint32_t cycles) {
+  return wrap([&](r0b200_ctx* c) {
+    R0_CHECK(buffers != nullptr && preflight != nullptr && mode <= 2, "witgen: bad argument");
+    R0_CHECK(buffers->data.rows == cycles && buffers->data.cols == 211 && buffers->global.cols == 90, "witgen: buffer shape");
+    struct Guard {
+      r0b200_trace* t;
+      ~Guard() { r0_trace_free(t); }
+    } g{r0_trace_upload(c, preflight, cycles, c->stream)};
+    const uint32_t checked = (buffers->data.checked ? 1u : 0u) | (buffers->global.checked ? 4u : 0u);
+    r0_witgen_rv32im(c, g.t, (uint32_t*)buffers->global.buf, (uint32_t*)buffers->data.buf, true, checked);
+  });
+}
+const char* risc0_circuit_rv32im_cuda_accum(const r0b200_raw_accum_buffers* buffers, const r0b200_preflight_trace* preflight,
+                                            uint32_t cycles) {
+  return wrap([&](r0b200_ctx* c) {
+    R0_CHECK(buffers != nullptr && preflight != nullptr, "accum: bad argument");
+    R0_CHECK(buffers->data.rows == cycles && buffers->accum.rows == cycles && buffers->accum.cols == 103, "accum: buffer shape");
+    struct Guard {
+      r0b200_trace* t;
+      ~Guard() { r0_trace_free(t); }
+    } g{r0_trace_upload(c, preflight, cycles, c->stream)};
+    const uint32_t checked = (buffers->data.checked ? 1u : 0u) | (buffers->accum.checked ? 2u : 0u) |
+                             (buffers->global.checked ? 4u : 0u) | (buffers->mix.checked ? 8u : 0u);
+    r0_accum_rv32im(c, g.t, (uint32_t*)buffers->data.buf, (uint32_t*)buffers->accum.buf, (uint32_t*)buffers->global.buf,
+                    (uint32_t*)buffers->mix.buf, true, checked);
+  });
+}
+
 const char* risc0_circuit_rv32im_cuda_eval_check(uint32_t* check, const uint32_t* ctrl, const uint32_t* data,
                                                  const uint32_t* accum, const uint32_t* mix, const uint32_t* out,
                                                  const uint32_t* rou, uint32_t po2, uint32_t domain,

@@ -73,6 +73,7 @@ void r0_eval_check_recursion(r0::Ctx* c, uint32_t* check, const uint32_t* accum,
 // rv32im witness generation / accumulation on the device (witgen.cu)
 r0b200_trace* r0_trace_upload(r0::Ctx* c, const r0b200_preflight_trace* trace_host, uint32_t cycles, cudaStream_t stream);
 void r0_trace_free(r0b200_trace* t);
-void r0_witgen_rv32im(r0::Ctx* c, r0b200_trace* t, uint32_t* global, uint32_t* data, bool sync_check);
+// checked: bit k = Buffer::checked of buffer k (0 data, 1 accum, 2 global, 3 mix); the reference's CPU path checks all
+void r0_witgen_rv32im(r0::Ctx* c, r0b200_trace* t, uint32_t* global, uint32_t* data, bool sync_check, uint32_t checked = 0xf);
 void r0_accum_rv32im(r0::Ctx* c, r0b200_trace* t, uint32_t* data, uint32_t* accum, uint32_t* global, uint32_t* mix,
-                     bool sync_check);
+                     bool sync_check, uint32_t checked = 0xf);

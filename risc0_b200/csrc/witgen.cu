@@ -223,14 +223,15 @@ void check_errors(Ctx* c, r0b200_trace* t, const char* what) {
   }
 }
 
-void upload_shared(Ctx* c, r0b200_trace* t, uint32_t* data, uint32_t* accum, uint32_t* global, uint32_t* mix, bool checked) {
+// checked: bit k = Buffer::checked of buffer k (BUF_DATA .. BUF_MIX)
+void upload_shared(Ctx* c, r0b200_trace* t, uint32_t* data, uint32_t* accum, uint32_t* global, uint32_t* mix, uint32_t checked) {
   WShared s;
   memset(&s, 0, sizeof(s));
   const uint32_t rows = t->cycles;
-  s.bufs[BUF_DATA] = WBuf{data, rows, R0_WG_KREGCOUNTDATA, checked ? 1u : 0u, 0};
-  s.bufs[BUF_ACCUM] = WBuf{accum, rows, R0_WG_KREGCOUNTACCUM, checked ? 1u : 0u, R0_WG_USER_ACCUM_SPLIT};
-  s.bufs[BUF_GLOBAL] = WBuf{global, 1, R0_WG_KREGCOUNTGLOBAL, checked ? 1u : 0u, 0};
-  s.bufs[BUF_MIX] = WBuf{mix, 1, R0_WG_KREGCOUNTMIX, checked ? 1u : 0u, 0};
+  s.bufs[BUF_DATA] = WBuf{data, rows, R0_WG_KREGCOUNTDATA, (checked >> BUF_DATA) & 1u, 0};
+  s.bufs[BUF_ACCUM] = WBuf{accum, rows, R0_WG_KREGCOUNTACCUM, (checked >> BUF_ACCUM) & 1u, R0_WG_USER_ACCUM_SPLIT};
+  s.bufs[BUF_GLOBAL] = WBuf{global, 1, R0_WG_KREGCOUNTGLOBAL, (checked >> BUF_GLOBAL) & 1u, 0};
+  s.bufs[BUF_MIX] = WBuf{mix, 1, R0_WG_KREGCOUNTMIX, (checked >> BUF_MIX) & 1u, 0};
   s.cycles = t->d_cycles;
   s.txns = t->d_txns;
   s.bigint_bytes = t->d_bigint;
@@ -293,9 +294,9 @@ void r0_trace_free(r0b200_trace* t) {
 
 // generate_witness: phase 1 = cycles [0, split) (they also count the u8 / u16 lookups), phase 2 = [split, cycles)
 // (the table cycles read the counters), ffi.cpp:284-296
-void r0_witgen_rv32im(Ctx* c, r0b200_trace* t, uint32_t* global, uint32_t* data, bool sync_check) {
+void r0_witgen_rv32im(Ctx* c, r0b200_trace* t, uint32_t* global, uint32_t* data, bool sync_check, uint32_t checked) {
   PhaseScope ph(c, "witgen", 4.0 * R0_WG_KREGCOUNTDATA * (double)t->cycles + 36.0 * t->cycles + 20.0 * t->txns_len);
-  upload_shared(c, t, data, nullptr, global, nullptr, true);
+  upload_shared(c, t, data, nullptr, global, nullptr, checked);
   R0_CUDA(cudaMemsetAsync(t->d_tables, 0, (256 + 65536) * 4, c->stream));
   const uint32_t n1 = t->split, n2 = t->cycles - t->split;
   if (n1) launch_step_exec(c->stream, t->d_shared, t->d_order, 0, n1);
@@ -307,9 +308,9 @@ void r0_witgen_rv32im(Ctx* c, r0b200_trace* t, uint32_t* global, uint32_t* data,
 
 // step_accum + prefix sums + back-propagation (ffi.cpp:316-365)
 void r0_accum_rv32im(Ctx* c, r0b200_trace* t, uint32_t* data, uint32_t* accum, uint32_t* global, uint32_t* mix,
-                     bool sync_check) {
+                     bool sync_check, uint32_t checked) {
   PhaseScope ph(c, "accum", 4.0 * (R0_WG_KREGCOUNTDATA + 2.0 * R0_WG_KREGCOUNTACCUM) * (double)t->cycles);
-  upload_shared(c, t, data, accum, global, mix, true);
+  upload_shared(c, t, data, accum, global, mix, checked);
   const uint32_t n = t->cycles, rows = t->cycles, cols = R0_WG_KREGCOUNTACCUM;
   launch_step_accum(c->stream, t->d_shared, t->d_order_all, n);
   const uint32_t nblocks = (n + SCAN_SEG - 1) / SCAN_SEG;

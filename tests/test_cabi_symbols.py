@@ -25,7 +25,8 @@ def test_library_exports_the_reference_symbol_table():
             "risc0_zkp_cuda_scatter", "risc0_zkp_cuda_sha_rows", "risc0_zkp_cuda_sha_fold", "risc0_zkp_cuda_combos_prepare",
             "sppark_init", "sppark_batch_expand", "sppark_batch_NTT", "sppark_batch_iNTT", "sppark_batch_zk_shift",
             "sppark_poseidon2_fold", "sppark_poseidon2_rows", "sppark_poseidon254_fold", "sppark_poseidon254_rows",
-            "supra_poly_divide", "risc0_circuit_rv32im_cuda_eval_check", "risc0_circuit_recursion_cuda_eval_check"}
+            "supra_poly_divide", "risc0_circuit_rv32im_cuda_eval_check", "risc0_circuit_recursion_cuda_eval_check",
+            "risc0_circuit_rv32im_cuda_witgen", "risc0_circuit_rv32im_cuda_accum"}
     assert want <= set(names), want - set(names)
     lib = _lib.load_library()
     for n in names:

@@ -124,3 +124,41 @@ def test_segment_upload_pipeline(hal):
     got1 = prover.prove_segment(s1)[0]
     again = prover.prove_segment(s0)[0]
     assert np.array_equal(got0, want[0]) and np.array_equal(got1, want[1]) and np.array_equal(again, want[0])
+
+
+def test_reference_witgen_symbols(hal):
+    # risc0_circuit_rv32im_cuda_witgen / _cuda_accum with the reference's structs (rv32im-sys/src/lib.rs:21-119),
+    # device buffers + host trace, as rv32im/src/prove/hal/cuda.rs:60-157 calls them
+    import ctypes as C
+    from risc0_b200 import _lib
+    from risc0_b200.hal import _trace_struct
+    L = C.CDLL(_lib.LIB_PATH)
+    L.risc0_circuit_rv32im_cuda_witgen.restype = C.c_char_p
+    L.risc0_circuit_rv32im_cuda_accum.restype = C.c_char_p
+    pf = PF.PreflightResults(seg("loop_po2_13"), (51, 52, 53, 54))
+    want_glob, want_data = W.ref_generate_witness(pf)
+    rows = pf.rows
+    data = hal.alloc_elem_init("data", 211 * rows, 0xFFFFFFFF)
+    hal.scatter(data, *pf.injector)
+    glob = hal.copy_from_elem("global", pf.global_)
+    hal.sync()
+    st, keep = _trace_struct(pf)
+
+    def rb(buf, r, c, checked=True):
+        return W.RawBuffer(buf.ptr.value, r, c, checked)
+
+    bufs = W.RawExecBuffers(rb(glob, 1, 90), rb(data, rows, 211))
+    err = L.risc0_circuit_rv32im_cuda_witgen(C.c_uint32(0), C.byref(bufs), C.byref(st), C.c_uint32(rows))
+    assert err is None, err
+    hal.eltwise_zeroize_elem(glob)
+    hal.eltwise_zeroize_elem(data)
+    assert np.array_equal(data.view(), want_data) and np.array_equal(glob.view(), want_glob)
+    mix_h = O.rand_elems(np.random.default_rng(6), 36)
+    accum = hal.alloc_elem_init("accum", 103 * rows, 0xFFFFFFFF)
+    mix = hal.copy_from_elem("mix", mix_h)
+    hal.sync()
+    ab = W.RawAccumBuffers(rb(data, rows, 211), rb(accum, rows, 103, False), rb(glob, 1, 90), rb(mix, 1, 36))
+    err = L.risc0_circuit_rv32im_cuda_accum(C.byref(ab), C.byref(st), C.c_uint32(rows))
+    assert err is None, err
+    hal.eltwise_zeroize_elem(accum)
+    assert np.array_equal(accum.view(), W.ref_accum(pf, want_glob, want_data, mix_h))
