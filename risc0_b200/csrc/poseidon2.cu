@@ -47,56 +47,83 @@ __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
   const uint32_t r = (uint32_t)mul_signed(x6, x1);
   return umin32(r, r + P);
 }
-__device__ __forceinline__ uint32_t dbl(uint32_t x) { return fp_add(x, x); }
-__device__ __forceinline__ uint32_t dbl_fma(uint32_t x) { return fp_add_fma(x, x); }
+// MODE selects, per group of linear-layer additions, which integer pipe they issue on (bit set = alu pipe as IADD3,
+// bit clear = fma pipe as IMAD x*1+y), and whether the round-constant addition is folded into the S-box input:
+//   bit 0: M_ext first stage (t0..t3 incl. doublings)   bit 1: M_ext second stage (t4..t7)
+//   bit 2: M_ext column sums                            bit 3: M_ext final "+ column sum"
+//   bit 4: partial-round sum tree                       bit 5: partial-round "+ sum"
+//   bit 6: round constants enter the S-box unreduced: x = c + rc - P in (-P, P) is a legal signed operand of the x^7
+//          chain, so the modular add (IADD3 + VIADDMNMX) becomes one IADD3
+// The best mask is measured (tools/bench_hash.py --mode, profiles/r2_poseidon2_modes.log); R0B200_P2_MODE overrides it.
+template <int MODE, int BIT>
+__device__ __forceinline__ uint32_t add_m(uint32_t a, uint32_t b) {
+  if (MODE & (1 << BIT)) return fp_add(a, b);
+  return fp_add_fma(a, b);
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t sbox7_rc(uint32_t x, uint32_t rc) {
+  if (MODE & 64) {
+    const int32_t x1 = (int32_t)(x + rc - P);   // in (-P, P)
+    const int32_t x2 = mul_signed(x1, x1);
+    const int32_t x4 = mul_signed(x2, x2);
+    const int32_t x6 = mul_signed(x4, x2);
+    const uint32_t r = (uint32_t)mul_signed(x6, x1);
+    return umin32(r, r + P);
+  }
+  return sbox7(fp_add(x, rc));
+}
 
 // M_ext = circ(2*M4, M4, ..., M4) with M4 the 4x4 matrix of poseidon2/mod.rs:139-151
+template <int MODE>
 __device__ __forceinline__ void m_ext(uint32_t (&c)[24]) {
   uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     uint32_t x0 = c[4 * i], x1 = c[4 * i + 1], x2 = c[4 * i + 2], x3 = c[4 * i + 3];
-    uint32_t t0 = fp_add_fma(x0, x1);
-    uint32_t t1 = fp_add_fma(x2, x3);
-    uint32_t t2 = fp_add_fma(dbl_fma(x1), t1);
-    uint32_t t3 = fp_add_fma(dbl_fma(x3), t0);
-    uint32_t t4 = fp_add_fma(dbl_fma(dbl_fma(t1)), t3);
-    uint32_t t5 = fp_add_fma(dbl_fma(dbl_fma(t0)), t2);
-    uint32_t t6 = fp_add_fma(t3, t5);
-    uint32_t t7 = fp_add_fma(t2, t4);
+    uint32_t t0 = add_m<MODE, 0>(x0, x1);
+    uint32_t t1 = add_m<MODE, 0>(x2, x3);
+    uint32_t t2 = add_m<MODE, 0>(add_m<MODE, 0>(x1, x1), t1);
+    uint32_t t3 = add_m<MODE, 0>(add_m<MODE, 0>(x3, x3), t0);
+    uint32_t t1d = add_m<MODE, 1>(t1, t1), t0d = add_m<MODE, 1>(t0, t0);
+    uint32_t t4 = add_m<MODE, 1>(add_m<MODE, 1>(t1d, t1d), t3);
+    uint32_t t5 = add_m<MODE, 1>(add_m<MODE, 1>(t0d, t0d), t2);
+    uint32_t t6 = add_m<MODE, 1>(t3, t5);
+    uint32_t t7 = add_m<MODE, 1>(t2, t4);
     c[4 * i] = t6;
     c[4 * i + 1] = t5;
     c[4 * i + 2] = t7;
     c[4 * i + 3] = t4;
-    s0 = fp_add_fma(s0, t6);
-    s1 = fp_add_fma(s1, t5);
-    s2 = fp_add_fma(s2, t7);
-    s3 = fp_add_fma(s3, t4);
+    s0 = add_m<MODE, 2>(s0, t6);
+    s1 = add_m<MODE, 2>(s1, t5);
+    s2 = add_m<MODE, 2>(s2, t7);
+    s3 = add_m<MODE, 2>(s3, t4);
   }
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    c[4 * i] = fp_add_fma(c[4 * i], s0);
-    c[4 * i + 1] = fp_add_fma(c[4 * i + 1], s1);
-    c[4 * i + 2] = fp_add_fma(c[4 * i + 2], s2);
-    c[4 * i + 3] = fp_add_fma(c[4 * i + 3], s3);
+    c[4 * i] = add_m<MODE, 3>(c[4 * i], s0);
+    c[4 * i + 1] = add_m<MODE, 3>(c[4 * i + 1], s1);
+    c[4 * i + 2] = add_m<MODE, 3>(c[4 * i + 2], s2);
+    c[4 * i + 3] = add_m<MODE, 3>(c[4 * i + 3], s3);
   }
 }
 
+template <int MODE>
 __device__ __forceinline__ void full_round(uint32_t (&c)[24], int r) {
 #pragma unroll
-  for (int i = 0; i < 24; i++) c[i] = sbox7(fp_add(c[i], c_rc_full[r * 24 + i]));
-  m_ext(c);
+  for (int i = 0; i < 24; i++) c[i] = sbox7_rc<MODE>(c[i], c_rc_full[r * 24 + i]);
+  m_ext<MODE>(c);
 }
 
+template <int MODE>
 __device__ __forceinline__ void partial_round(uint32_t (&c)[24], int r) {
-  c[0] = sbox7(fp_add(c[0], c_rc_partial[r]));
+  c[0] = sbox7_rc<MODE>(c[0], c_rc_partial[r]);
   // sum of 24 canonical values: pairwise tree keeps the dependency chain short
   uint32_t p[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) p[i] = fp_add_fma(c[2 * i], c[2 * i + 1]);
+  for (int i = 0; i < 12; i++) p[i] = add_m<MODE, 4>(c[2 * i], c[2 * i + 1]);
 #pragma unroll
-  for (int i = 0; i < 6; i++) p[i] = fp_add_fma(p[2 * i], p[2 * i + 1]);
-  uint32_t sum = fp_add_fma(fp_add_fma(fp_add_fma(p[0], p[1]), fp_add_fma(p[2], p[3])), fp_add_fma(p[4], p[5]));
+  for (int i = 0; i < 6; i++) p[i] = add_m<MODE, 4>(p[2 * i], p[2 * i + 1]);
+  uint32_t sum = add_m<MODE, 4>(add_m<MODE, 4>(add_m<MODE, 4>(p[0], p[1]), add_m<MODE, 4>(p[2], p[3])), add_m<MODE, 4>(p[4], p[5]));
   // sum + diag_i * c_i. diag_i is a constant, so Shoup's method applies: q = hi(c * floor(d 2^32 / P)), r = c*d - q*P in
   // [0, 2P) using only the LOW 32 bits of both products: IMAD.HI + 2 IMAD = 8 fma-pipe cycles instead of the 10 of a
   // Montgomery product (IMAD.WIDE and IMAD.HI issue at quarter rate on sm_100a, profiles/r1_int_pipe_rates.log).
@@ -105,21 +132,27 @@ __device__ __forceinline__ void partial_round(uint32_t (&c)[24], int r) {
     const uint32_t q = __umulhi(c[i], c_diag_q[i]);
     uint32_t r = c[i] * c_diag_n[i] - q * P;
     r = umin32(r, r - P);
-    c[i] = fp_add(r, sum);
+    c[i] = (MODE & 32) ? fp_add(r, sum) : fp_add_fma(r, sum);
   }
 }
 
-__device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) {
-  m_ext(c);
+template <int MODE>
+__device__ __forceinline__ void p2_permute_m(uint32_t (&c)[24]) {
+  m_ext<MODE>(c);
 #pragma unroll 1
-  for (int r = 0; r < 4; r++) full_round(c, r);
+  for (int r = 0; r < 4; r++) full_round<MODE>(c, r);
 #pragma unroll 1
-  for (int r = 0; r < 21; r++) partial_round(c, r);
+  for (int r = 0; r < 21; r++) partial_round<MODE>(c, r);
 #pragma unroll 1
-  for (int r = 4; r < 8; r++) full_round(c, r);
+  for (int r = 4; r < 8; r++) full_round<MODE>(c, r);
 }
+#ifndef R0_P2_DEFAULT_MODE
+#define R0_P2_DEFAULT_MODE 32   // round-1 schedule: everything on the fma pipe except the partial round's "+ sum"
+#endif
+__device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) { p2_permute_m<R0_P2_DEFAULT_MODE>(c); }
 
 // out[row] = sponge over matrix[j*rows + row], j < cols (overwrite mode, zero-filled tail, empty input = one permute)
+template <int MODE>
 __global__ void __launch_bounds__(256) p2_hash_rows_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix,
                                                          size_t rows, uint32_t cols) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,7 +170,7 @@ __global__ void __launch_bounds__(256) p2_hash_rows_kernel(uint32_t* __restrict_
 #pragma unroll
       for (int i = 0; i < 16; i++) c[i] = (done + i < cols) ? matrix[(size_t)(done + i) * rows + row] : 0u;
     }
-    p2_permute(c);
+    p2_permute_m<MODE>(c);
     done += 16;
   } while (done < cols);
   uint4* o = reinterpret_cast<uint4*>(out + row * 8);
@@ -244,7 +277,15 @@ void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows,
   PhaseScope ph(c, "hash_rows", 4.0 * (double)rows * (double)cols + 32.0 * (double)rows);
   if (rows == 0) return;
   R0_CHECK(cols <= 0xffffffffull, "hash_rows: too many columns");
-  p2_hash_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols);
+  static const int mode = getenv("R0B200_P2_MODE") ? atoi(getenv("R0B200_P2_MODE")) : R0_P2_DEFAULT_MODE;
+  const unsigned grid = (unsigned)((rows + 255) / 256);
+#define P2_ROWS(M) case M: p2_hash_rows_kernel<M><<<grid, 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
+  switch (mode) {
+    P2_ROWS(0) P2_ROWS(8) P2_ROWS(32) P2_ROWS(40) P2_ROWS(64) P2_ROWS(72) P2_ROWS(96) P2_ROWS(104) P2_ROWS(112) P2_ROWS(120)
+    P2_ROWS(100) P2_ROWS(108) P2_ROWS(124) P2_ROWS(127) P2_ROWS(63) P2_ROWS(98) P2_ROWS(106) P2_ROWS(122) P2_ROWS(116)
+    default: throw std::invalid_argument("R0B200_P2_MODE: mask not compiled in");
+  }
+#undef P2_ROWS
   count_launch(c);
   R0_CUDA(cudaGetLastError());
 }
