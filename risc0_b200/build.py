@@ -126,7 +126,11 @@ def build(force=False, verbose=False, jobs=None):
     for src in sources():
         obj = os.path.join(OBJ, os.path.relpath(src, CSRC).replace(os.sep, "_")[:-3] + ".o")
         objs.append(obj)
-        dep_time = wg_time if os.path.basename(src).startswith("witgen") else hdr_time
+        base = os.path.basename(src)
+        if base in SLOW_SOURCES:      # include only the witgen runtime, fp.cuh and the generated step functions
+            dep_time = max(os.path.getmtime(os.path.join(CSRC, f)) for f in ("witgen_rt.cuh", "fp.cuh", "gen/witgen_rv32im.inc"))
+        else:
+            dep_time = wg_time if base.startswith("witgen") else hdr_time
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), dep_time):
             todo.append((src, obj))
     todo.sort(key=lambda so: os.path.basename(so[0]) not in SLOW_SOURCES)   # start the slow ones first

@@ -290,8 +290,7 @@ r0b200_err r0b200_mix_poly_coeffs(r0b200_ctx* ctx, uint32_t* out, const uint32_t
 r0b200_err r0b200_batch_evaluate_any(r0b200_ctx* ctx, const uint32_t* coeffs, size_t poly_count, uint32_t lg_n,
                                      const uint32_t* which, const uint32_t* xs, uint32_t* out, size_t eval_count) {
   CTX_BEGIN
-  (void)poly_count;
-  r0_batch_evaluate_any(ctx, coeffs, size_t(1) << lg_n, which, xs, out, eval_count);
+  r0_batch_evaluate_any(ctx, coeffs, size_t(1) << lg_n, which, xs, out, eval_count, poly_count);
   R0_API_END
 }
 r0b200_err r0b200_gather_sample(r0b200_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size,

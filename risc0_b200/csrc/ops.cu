@@ -526,9 +526,12 @@ void r0_mix_poly_coeffs(Ctx* c, uint32_t* out, const FpExt& mix_start, const FpE
   }
 }
 
+// distinct_polys: how many different polynomials the evaluations touch (SURVEY 8d counts 4 * P_distinct * n algorithmic
+// bytes: evaluations of one register at several back-points re-read its polynomial through L2, not HBM); 0 = unknown
 void r0_batch_evaluate_any(Ctx* c, const uint32_t* coeffs, size_t n, const uint32_t* which_dev, const uint32_t* xs_dev,
-                           uint32_t* out_dev, size_t eval_count) {
-  PhaseScope ph(c, "batch_evaluate_any", 4.0 * (double)n * (double)eval_count);
+                           uint32_t* out_dev, size_t eval_count, size_t distinct_polys) {
+  const size_t distinct = distinct_polys && distinct_polys < eval_count ? distinct_polys : eval_count;
+  PhaseScope ph(c, "batch_evaluate_any", 4.0 * (double)n * (double)distinct);
   if (eval_count == 0) return;
   const size_t per_block = (size_t)EV_T * EV_CH;
   const int nchunks = (int)((n + per_block - 1) / per_block);

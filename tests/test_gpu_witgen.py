@@ -162,3 +162,17 @@ def test_reference_witgen_symbols(hal):
     assert err is None, err
     hal.eltwise_zeroize_elem(accum)
     assert np.array_equal(accum.view(), W.ref_accum(pf, want_glob, want_data, mix_h))
+
+
+def test_scheduler_on_device(hal):
+    # the r0vm-style scheduler over the real prover (one device here; tools/bench_schedule.py runs it over several):
+    # three segments of one continuation, seals equal the direct proofs, results in submission order
+    from risc0_b200.scheduler import b200_scheduler
+    segs = PF.execute(PF.simple_loop_kernel(6000), segment_po2=13)[:3]
+    assert len(segs) == 3
+    rand_z = (61, 62, 63, 64)
+    res = b200_scheduler([0], rand_z=rand_z).run(segs)
+    prover = SegmentProver(hal)
+    for s, r in zip(segs, res):
+        assert np.array_equal(r.seal, prover.prove_core(PF.PreflightResults(s, rand_z))[0])
+    assert [r.index for r in res] == [0, 1, 2]

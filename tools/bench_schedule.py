@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""S segments over G GPUs in ONE process (risc0_b200/scheduler.py: threads, one B200Hal per device, shared GPU queue) -
+BASELINE config 3's shape (multi-segment continuation sharded across the GPUs of a box) with S not a multiple of G.
+
+    python tools/bench_schedule.py [--po2 18] [--segments 5] [--gpus 2]
+
+Segments are the first S segments of one long loop-guest session (real continuation: segment s + 1 starts from the
+memory image segment s left). Prints one JSON line: total user cycles / wall, per-device counts, and whether every seal
+equals the one a single device produces for the same segment."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from risc0_b200 import B200Hal, SegmentProver  # noqa: E402
+from risc0_b200 import preflight as PF  # noqa: E402
+from risc0_b200.scheduler import b200_scheduler  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--po2", type=int, default=18)
+    ap.add_argument("--segments", type=int, default=5)
+    ap.add_argument("--gpus", type=int, default=2)
+    ap.add_argument("--check", action="store_true", help="re-prove every segment on device 0 alone and compare seals")
+    a = ap.parse_args()
+    t0 = time.perf_counter()
+    segs = PF.execute(PF.simple_loop_kernel(1 << 30), segment_po2=a.po2, max_segments=a.segments, max_cycles=1 << 40)
+    t_exec = time.perf_counter() - t0
+    rand_z = (11, 22, 33, 44)
+    # warm every device once (module load, pool growth) so the timed run is steady state
+    sched = b200_scheduler(list(range(a.gpus)), rand_z=rand_z, cpu_workers=2)
+    sched.run(segs[:a.gpus])
+    sched = b200_scheduler(list(range(a.gpus)), rand_z=rand_z, cpu_workers=2)
+    t0 = time.perf_counter()
+    res = sched.run(segs)
+    wall = time.perf_counter() - t0
+    cycles = sum(s.suspend_cycle for s in segs)
+    out = {"po2": a.po2, "segments": len(segs), "gpus": a.gpus, "wall_s": round(wall, 3), "user_cycles": cycles,
+           "cycles_per_s": round(cycles / wall), "per_device": {str(w.device): w.proved for w in sched.workers},
+           "device_busy_s": {str(w.device): round(w.busy_s, 3) for w in sched.workers},
+           "preflight_s": [round(r.t_preflight, 2) for r in res], "prove_s": [round(r.t_prove, 3) for r in res],
+           "executor_s": round(t_exec, 2),
+           "note": "wall includes the plain-Python preflight of every segment (2 workers), which is what bounds it here"}
+    if a.check:
+        hal = B200Hal(0)
+        p = SegmentProver(hal)
+        same = [bool(np.array_equal(p.prove_core(PF.PreflightResults(s, rand_z))[0], r.seal)) for s, r in zip(segs, res)]
+        hal.close()
+        out["seals_equal_single_device"] = same
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
