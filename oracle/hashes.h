@@ -8,7 +8,7 @@
 // byte-swapped state words), :79-98 (compress = hash_pair), sha/rng.rs:27-101 (ShaRng) and
 // baby_bear.rs:109-139 (Elem::random: six u32 folded mod P).
 // Pinned by KATs: permutation + hash KATs poseidon2/mod.rs:330-401, RNG KAT prove/merkle.rs:161-172,
-// SHA hash_rows KAT hal/cpu.rs:726-733 (tests/test_oracle_hashes.py).
+// SHA hash_rows KAT hal/cpu.rs:726-733 (tests/test_oracle_kats.py).
 #pragma once
 #include <array>
 #include <cstring>

@@ -68,6 +68,9 @@ struct Ctx {
   };
   std::vector<PhaseRec> phase_log;
   std::vector<cudaEvent_t> event_pool;
+  // auxiliary streams / events of the concurrent-tiled eval_check mode (created on demand, gen/eval_check_*.cu)
+  std::vector<cudaStream_t> aux_streams;
+  std::vector<cudaEvent_t> aux_events;
 };
 
 // RAII phase marker used by the launchers; free when profiling is off.

@@ -58,6 +58,8 @@ void r0b200_destroy(r0b200_ctx* c) {
     cudaEventDestroy(r.b);
   }
   for (auto& e : c->event_pool) cudaEventDestroy(e);
+  for (auto& e : c->aux_events) cudaEventDestroy(e);
+  for (auto& st : c->aux_streams) cudaStreamDestroy(st);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   cudaStreamDestroy(c->copy_stream);

@@ -10,7 +10,8 @@ import sys
 
 import numpy as np
 
-os.environ.setdefault("R0B200_PROFILE_PARTS", "1")
+if "R0B200_EVAL_TILED" not in os.environ:
+    os.environ.setdefault("R0B200_PROFILE_PARTS", "1")
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from risc0_b200 import B200Hal  # noqa: E402
@@ -46,6 +47,9 @@ def main():
     res["lib"] = os.environ.get("R0B200_LIB", "default")
     res["po2"] = a.po2
     res["ns_per_point"] = round(ph["eval_check"]["ms"] / a.iters * 1e6 / domain, 2)
+    import zlib
+    res["check_crc32"] = zlib.crc32(check.view().tobytes())
+    res["mode"] = {k: os.environ[k] for k in ("R0B200_EVAL_TILED", "R0B200_EVAL_STREAMS", "R0B200_EVAL_AHEAD") if k in os.environ}
     print(json.dumps(res), flush=True)
 
 

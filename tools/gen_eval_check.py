@@ -1092,6 +1092,16 @@ cudaKernel_t g_kernels[kParts];
 std::once_flag g_once;
 std::string g_load_error;
 
+// sum of the per-part partial results of one point tile: check[k][i] = sum_j partial[j][k][i]   (concurrent-tiled mode)
+__global__ void k_reduce_partials(uint32_t* check, const uint32_t* partial, int nparts, size_t domain, size_t i0, size_t npts) {
+  const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= 4 * npts) return;
+  const size_t k = w / npts, i = i0 + w %% npts;
+  uint32_t acc = 0;
+  for (int j = 0; j < nparts; j++) acc = fp_add(acc, partial[((size_t)j * 4 + k) * domain + i]);
+  check[k * domain + i] = acc;
+}
+
 void load_kernels() {
   const void* images[kParts] = {%(images)s};
   const char* names[kParts] = {%(names)s};
@@ -1153,8 +1163,63 @@ void r0_eval_check_%(name)s(Ctx* c, uint32_t* check, const uint32_t* accum, cons
   // 2^16 points keeps its tap columns (83 MB for rv32im) in L2 for the later parts and cuts DRAM traffic ~15x, but the
   // 512-block launches it needs run at well under full occupancy: measured 26.1 ms per 2^20 points against 16.2 ms
   // untiled (2^17: 21.0, 2^15: 35.3; gpurun_out/evalcheck_variants12.log), so it is off.
-  const size_t tile = std::min<size_t>(domain, size_t(1) << %(tile_lg)d);
   uint32_t domain32 = (uint32_t)domain;
+  // Concurrent-tiled mode (R0B200_EVAL_TILED=<lg of the point tile>, off by default - see DESIGN.md 3.4 for the
+  // measurement): all parts of one tile run CONCURRENTLY on a few auxiliary streams, each storing into its own partial
+  // buffer (planes of `domain` words, so the kernels need no change), and a small kernel sums the partials of the tile
+  // into `check`. The tile's tap columns are then touched by all parts within the same window and stay in L2, while
+  // the launches in flight together still fill the GPU - which the sequential tiling below cannot do.
+  static const int tiled_lg = getenv("R0B200_EVAL_TILED") ? atoi(getenv("R0B200_EVAL_TILED")) : 0;
+  static const int nstreams = getenv("R0B200_EVAL_STREAMS") ? atoi(getenv("R0B200_EVAL_STREAMS")) : 8;
+  static const int max_ahead = getenv("R0B200_EVAL_AHEAD") ? atoi(getenv("R0B200_EVAL_AHEAD")) : 1;
+  if (tiled_lg >= 10 && domain > (size_t(1) << tiled_lg) && nstreams >= 1 && nstreams <= 32) {
+    const size_t tile_pts = size_t(1) << tiled_lg;
+    const size_t ntiles = domain / tile_pts;
+    while ((int)c->aux_streams.size() < nstreams) {
+      cudaStream_t st;
+      R0_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      c->aux_streams.push_back(st);
+    }
+    // events: [0] = start, then per (tile parity, stream) "parts done", then per tile slot "reduced"
+    const size_t nev = 1 + 2 * (size_t)nstreams + (size_t)(max_ahead + 1);
+    while (c->aux_events.size() < nev) {
+      cudaEvent_t ev;
+      R0_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      c->aux_events.push_back(ev);
+    }
+    uint32_t* partial = nullptr;
+    R0_CUDA(cudaMallocAsync(&partial, (size_t)kParts * 4 * domain * 4, c->stream));
+    R0_CUDA(cudaEventRecord(c->aux_events[0], c->stream));
+    for (int s = 0; s < nstreams; s++) R0_CUDA(cudaStreamWaitEvent(c->aux_streams[s], c->aux_events[0], 0));
+    const unsigned blocks = (unsigned)((tile_pts + threads - 1) / threads);
+    uint32_t first = 1u;
+    for (size_t t = 0; t < ntiles; t++) {
+      uint32_t base = (uint32_t)(t * tile_pts);
+      // bound the drift: the part streams may run at most `max_ahead` tiles ahead of the reduction
+      if (t > (size_t)max_ahead) {
+        cudaEvent_t red = c->aux_events[1 + 2 * nstreams + (t - 1 - max_ahead) %% (max_ahead + 1)];
+        for (int s = 0; s < nstreams; s++) R0_CUDA(cudaStreamWaitEvent(c->aux_streams[s], red, 0));
+      }
+      for (int j = 0; j < kParts; j++) {
+        uint32_t* out = partial + (size_t)j * 4 * domain;
+        void* args[] = {&out, &accum, &code, &data, &domain32, &first, &base, &k};
+        R0_CUDA(cudaLaunchKernel((const void*)g_kernels[j], dim3(blocks), dim3(threads), args, 0, c->aux_streams[j %% nstreams]));
+        count_launch(c);
+      }
+      for (int s = 0; s < nstreams; s++) {
+        cudaEvent_t ev = c->aux_events[1 + (t & 1) * nstreams + s];
+        R0_CUDA(cudaEventRecord(ev, c->aux_streams[s]));
+        R0_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
+      }
+      k_reduce_partials<<<(unsigned)((4 * tile_pts + 255) / 256), 256, 0, c->stream>>>(check, partial, kParts, domain, t * tile_pts, tile_pts);
+      count_launch(c);
+      R0_CUDA(cudaEventRecord(c->aux_events[1 + 2 * nstreams + t %% (max_ahead + 1)], c->stream));
+    }
+    R0_CUDA(cudaGetLastError());
+    R0_CUDA(cudaFreeAsync(partial, c->stream));
+    return;
+  }
+  const size_t tile = std::min<size_t>(domain, size_t(1) << %(tile_lg)d);
   static const bool profile_parts = getenv("R0B200_PROFILE_PARTS") != nullptr;  // per-part timing is opt-in
   for (size_t i0 = 0; i0 < domain; i0 += tile) {
     const size_t npts = std::min(tile, domain - i0);
