@@ -1545,11 +1545,11 @@ class PreflightResults:
 
 # ---- a tiny assembler for hand-written guests (execute/testutil.rs:186-348) ------------------------------------------
 class Assembler:
-    def __init__(self):
-        self.text, self.data = [], {}
+    def __init__(self, base=USER_START_ADDR + WORD_SIZE):
+        self.text, self.data, self.base = [], {}, base
 
     def program(self):
-        entry = USER_START_ADDR + WORD_SIZE
+        entry = self.base
         image = {entry + 4 * i: w for i, w in enumerate(self.text)}
         image.update(self.data)
         return entry, image
@@ -1623,6 +1623,9 @@ class Assembler:
     def ecall(self):
         self._i(0, 0, 0, 0, 0b1110011)
 
+    def mret(self):
+        self.text.append(0x30200073)
+
     def host_terminate(self, a0, a1):
         self.li(REG_A7, HOST_ECALL_TERMINATE)
         self.li(REG_A0, a0)
@@ -1648,3 +1651,32 @@ def simple_loop_kernel(count):
     asm.host_terminate(0, 0)
     entry, image = asm.program()
     return MemoryImage.new_kernel(entry, image)
+
+
+def user_mode_guest(count=20):
+    """a user-mode loop under a minimal machine-mode kernel: the kernel's entry points MEPC at the user program and
+    `mret`s into it; the user program counts and issues `ecall`, which traps to the kernel's dispatch address
+    (ECALL_DISPATCH_ADDR, r0vm.rs:372-381), whose handler terminates. Exercises the user register file, USER_ECALL and
+    MRET control cycles and the machine-mode switches."""
+    a4, a5, t0, t1 = 14, 15, 5, 6
+    user = Assembler()
+    user.addi(a4, 0, 0)
+    user.li(a5, count)
+    user.addi(a4, a4, 1)
+    user.blt(a4, a5, -4)
+    user.ecall()
+    user_entry, user_image = user.program()
+    kern = Assembler(base=KERNEL_START_ADDR)
+    kern.li(t1, user_entry - 4)          # mret resumes at MEPC + 4
+    kern.li(t0, MEPC_ADDR)
+    kern.sw(t1, t0, 0)
+    kern.mret()
+    handler = KERNEL_START_ADDR + 0x100
+    while KERNEL_START_ADDR + 4 * len(kern.text) < handler:
+        kern.text.append(0x00000013)     # nop
+    kern.host_terminate(0, 0)
+    kentry, kimage = kern.program()
+    image = dict(user_image)
+    image.update(kimage)
+    image[ECALL_DISPATCH_ADDR] = handler
+    return MemoryImage.new_kernel(kentry, image)

@@ -138,6 +138,16 @@ def test_every_instruction_kind_and_host_read():
         assert want in majors, want
 
 
+def test_user_mode_guest_with_kernel_traps():
+    # user-mode code under a machine-mode kernel: mret into user mode, user ecall -> kernel dispatch -> terminate
+    segs = PF.execute(PF.user_mode_guest(30), segment_po2=14)
+    assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
+    pf, _, _, _ = check_segment(segs[0], seed=4)
+    kinds = set(zip(pf.cycles["major"].tolist(), pf.cycles["minor"].tolist()))
+    assert (7, 2) in kinds and (7, 3) in kinds          # CONTROL0: USER_ECALL and MRET
+    assert set(pf.cycles["machine_mode"].tolist()) >= {0, 1}
+
+
 def test_injector_and_globals_shape():
     segs = PF.execute(PF.simple_loop_kernel(50), segment_po2=13)
     pf = PF.PreflightResults(segs[0], (1, 2, 3, 4))
