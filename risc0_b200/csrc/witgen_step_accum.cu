@@ -9,7 +9,10 @@ namespace {   // internal linkage: both step translation units instantiate the s
 #include "gen/witgen_rv32im.inc"
 }  // namespace
 
-__global__ void __launch_bounds__(128) k_step_accum(const WShared* s, const uint32_t* order, uint32_t count) {
+#ifndef WG_MIN_BLOCKS
+#define WG_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, WG_MIN_BLOCKS) k_step_accum(const WShared* s, const uint32_t* order, uint32_t count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const uint32_t cycle = order[i];
