@@ -49,8 +49,9 @@ def generate(force=False):
         irf = os.path.join(HERE, "circuits", name + ".ir.json.gz")
         launcher = os.path.join(CSRC, "gen", "eval_check_%s.cu" % name)
         ptx = glob.glob(os.path.join(CSRC, "gen", "eval_check_%s_p*.ptx" % name))
-        newest_in = max(os.path.getmtime(gen), os.path.getmtime(irf),
-                        os.path.getmtime(os.path.join(root, "tools", "circuit_ir.py")))
+        newest_in = max([os.path.getmtime(gen), os.path.getmtime(irf),
+                         os.path.getmtime(os.path.join(root, "tools", "circuit_ir.py"))] +
+                        [os.path.getmtime(f) for f in glob.glob(os.path.join(HERE, "circuits", name + ".tune.json"))])
         if force or not ptx or not os.path.exists(launcher) or min(os.path.getmtime(f) for f in ptx) < newest_in:
             r = subprocess.run([sys.executable, gen, name, "--from-ir"], capture_output=True, text=True)
             if r.returncode != 0:
@@ -76,7 +77,19 @@ SLOW_SOURCES = {"witgen_step_exec.cu": ["-Xptxas", "-O1", "-diag-suppress", "550
 
 
 def _ptxas(ptx, cubin, flags):
-    cmd = [os.path.join(os.path.dirname(NVCC), "ptxas"), "-arch=sm_100a", "-v"] + flags + [ptx, "-o", cubin]
+    # ptxas ignores -maxrregcount for entries that carry .maxntid (all generated kernels do): a register cap has to be
+    # the kernel's own .maxnreg directive, so the flag is turned into one on a temporary copy of the PTX.
+    cap = [f for f in flags if f.startswith("-maxrregcount=")]
+    src = ptx
+    if cap:
+        flags = [f for f in flags if f not in cap]
+        text = open(ptx).read()
+        if ".maxnreg" not in text:
+            text = text.replace("\n{", "\n.maxnreg %d\n{" % int(cap[-1].split("=")[1]), 1)
+        src = cubin[:-6] + ".capped.ptx"
+        with open(src, "w") as f:
+            f.write(text)
+    cmd = [os.path.join(os.path.dirname(NVCC), "ptxas"), "-arch=sm_100a", "-v"] + flags + [src, "-o", cubin]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("ptxas failed for %s:\n%s\n%s" % (ptx, r.stdout, r.stderr))
@@ -86,6 +99,23 @@ def _ptxas(ptx, cubin, flags):
     return int(m.group(1)) if m else 0, int(regs.group(1)) if regs else 0, r.stderr
 
 
+_TUNED = None
+
+
+def _tuned_flags():
+    """kernel name -> ptxas flags, the fastest of the measured flag sets for that part (risc0_b200/circuits/*.tune.json,
+    written by tools/autotune_eval_check.py from per-part device times at po2 = 20). All flag sets assemble the same PTX,
+    so results are bit-identical whichever is chosen."""
+    global _TUNED
+    if _TUNED is None:
+        import json
+        _TUNED = {}
+        if os.environ.get("R0B200_NO_TUNED") != "1":
+            for f in glob.glob(os.path.join(HERE, "circuits", "*.tune.json")):
+                _TUNED.update(json.load(open(f))["flags"])
+    return _TUNED
+
+
 SPILL_LIMIT = 4000  # bytes of spill stores per thread above which the -O3 schedule loses to the -O1 one (measured)
 
 
@@ -93,14 +123,18 @@ def _assemble(ptx, cubin, verbose):
     """Generated straight-line kernels: ptxas -O3 schedules them well when the register pressure of the part is low,
     but on the high-pressure parts its pre-allocation scheduler hoists loads across tens of thousands of instructions
     and the allocator falls back to spilling nearly everything. Those parts are assembled with -O1 (program order
-    kept) under a 128-register cap for twice the occupancy. Measured per part in gpurun_out/evalcheck_variants*.log."""
-    if PTXAS_OPT != "-O3":
+    kept). This heuristic only applies to parts without a measured entry in circuits/*.tune.json. Measured per part in gpurun_out/evalcheck_variants*.log."""
+    if PTXAS_OPT != "-O3" or PTXAS_EXTRA:          # experiment builds: exactly the flags asked for, for every part
         spill, regs, log = _ptxas(ptx, cubin, [PTXAS_OPT] + PTXAS_EXTRA)
+        return ptx, log
+    tuned = _tuned_flags().get(os.path.basename(ptx)[:-4])
+    if tuned is not None:                          # measured per part on the B200 (tools/autotune_eval_check.py)
+        spill, regs, log = _ptxas(ptx, cubin, tuned)
         return ptx, log
     spill, regs, log = _ptxas(ptx, cubin, ["-O3"])
     if spill > SPILL_LIMIT or regs <= 64:
-        spill1, regs1, log1 = _ptxas(ptx, cubin, ["-O1", "-maxrregcount=128"])
-        log += "-> re-assembled with -O1 -maxrregcount=128:\n" + log1
+        spill1, regs1, log1 = _ptxas(ptx, cubin, ["-O1"])
+        log += "-> re-assembled with -O1:\n" + log1
     return ptx, log
 
 
@@ -138,7 +172,7 @@ def build(force=False, verbose=False, jobs=None):
     ptx_todo, cubins = [], []
     # the ptxas flag set is part of the cubin staleness key
     stamp = os.path.join(OBJ, "ptxas_flags.stamp")
-    flag_key = repr((PTXAS_OPT, PTXAS_EXTRA, SPILL_LIMIT))
+    flag_key = repr((PTXAS_OPT, PTXAS_EXTRA, SPILL_LIMIT, sorted(_tuned_flags().items())))
     flags_changed = not os.path.exists(stamp) or open(stamp).read() != flag_key
     for ptx in ptx_sources():
         cubin = os.path.join(OBJ, os.path.basename(ptx)[:-4] + ".cubin")

@@ -22,6 +22,7 @@ __constant__ uint32_t c_diag[24];
 __constant__ uint32_t c_diag_n[24];   // M_INT_DIAG_HZN in NORMAL form: x~ * d mod P keeps x~'s Montgomery form
 __constant__ uint32_t c_diag_q[24];   // floor(d * 2^32 / P): Shoup's precomputed quotient for multiplying by the constant d
 __constant__ uint32_t c_one;  // = 1, opaque to the compiler: a * c_one + b is an IMAD, i.e. an add on the fma pipe
+__constant__ uint32_t c_zero;  // = 0, opaque to the compiler: a + b + c_zero is a genuine three-input IADD3 (alu pipe)
 
 // The permutation is bound by the alu pipe (every modular add / product ends in a VIADDMNMX there), while the fma pipe
 // is half idle; adds in the linear layer are therefore issued as IMAD (x * 1 + y) to balance the two pipes.
@@ -30,21 +31,38 @@ __device__ __forceinline__ uint32_t fp_add_fma(uint32_t a, uint32_t b) {
   return umin32(r, r - P);
 }
 
+// ptxas balances INSTRUCTION COUNTS between the two integer pipes on its own: it rewrites plain two-input adds as
+// IMAD.IADD (fma pipe) or LEA / IADD3 (alu pipe) whichever way they are written in C. It does not know that
+// IMAD.WIDE / IMAD.HI hold the fma pipe for 4 cycles, so it leaves that pipe over-committed. A three-input add cannot
+// become an IMAD, so this form pins an addition to the alu pipe.
+__device__ __forceinline__ uint32_t fp_add_alu(uint32_t a, uint32_t b) {
+  uint32_t r;   // inline PTX so that the front end cannot share (a + c_zero) between sums and leave two-input adds behind
+  asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(r) : "r"(a), "r"(b), "r"(c_zero));
+  return umin32(r, r - P);
+}
+
 // Signed Montgomery product: for |a|, |b| < P the result is in (-P, P) and congruent to a*b/2^32 - exact because the
 // low words of t and m*P cancel. Inside the x^7 chain the intermediate powers never meet an addition, so they can stay
 // in this non-canonical signed form and only x^7 pays the "conditional add P" (one VIADDMNMX instead of four on the
 // alu pipe, which is the pipe that bounds the permutation).
+template <bool ALU = false>
 __device__ __forceinline__ int32_t mul_signed(int32_t a, int32_t b) {
   const int64_t t = (int64_t)a * b;
   const int32_t m = (int32_t)((uint32_t)t * MONT_PINV);
+  if (ALU) {   // three inputs: stays an IADD3
+    int32_t r;
+    asm("{ .reg .s32 t; sub.s32 t, %1, %2; add.s32 %0, t, %3; }" : "=r"(r) : "r"((int32_t)(t >> 32)), "r"(__mulhi(m, (int32_t)P)), "r"((int32_t)c_zero));
+    return r;
+  }
   return (int32_t)(t >> 32) - __mulhi(m, (int32_t)P);
 }
+template <bool ALU = false>
 __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
   const int32_t x1 = (int32_t)x;
-  const int32_t x2 = mul_signed(x1, x1);
-  const int32_t x4 = mul_signed(x2, x2);
-  const int32_t x6 = mul_signed(x4, x2);
-  const uint32_t r = (uint32_t)mul_signed(x6, x1);
+  const int32_t x2 = mul_signed<ALU>(x1, x1);
+  const int32_t x4 = mul_signed<ALU>(x2, x2);
+  const int32_t x6 = mul_signed<ALU>(x4, x2);
+  const uint32_t r = (uint32_t)mul_signed<ALU>(x6, x1);
   return umin32(r, r + P);
 }
 // MODE selects, per group of linear-layer additions, which integer pipe they issue on (bit set = alu pipe as IADD3,
@@ -57,19 +75,23 @@ __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
 // The best mask is measured (tools/bench_hash.py --mode, profiles/r2_poseidon2_modes.log); R0B200_P2_MODE overrides it.
 template <int MODE, int BIT>
 __device__ __forceinline__ uint32_t add_m(uint32_t a, uint32_t b) {
+  if (MODE & 128) return fp_add_alu(a, b);
   if (MODE & (1 << BIT)) return fp_add(a, b);
   return fp_add_fma(a, b);
 }
 template <int MODE>
 __device__ __forceinline__ uint32_t sbox7_rc(uint32_t x, uint32_t rc) {
   if (MODE & 64) {
-    const int32_t x1 = (int32_t)(x + rc - P);   // in (-P, P)
-    const int32_t x2 = mul_signed(x1, x1);
-    const int32_t x4 = mul_signed(x2, x2);
-    const int32_t x6 = mul_signed(x4, x2);
-    const uint32_t r = (uint32_t)mul_signed(x6, x1);
+    int32_t x1 = (int32_t)(x + rc - P);   // in (-P, P)
+    if (MODE & 128) asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(x1) : "r"(x), "r"(rc), "r"(c_zero - P));
+    constexpr bool A = (MODE & 128) != 0;
+    const int32_t x2 = mul_signed<A>(x1, x1);
+    const int32_t x4 = mul_signed<A>(x2, x2);
+    const int32_t x6 = mul_signed<A>(x4, x2);
+    const uint32_t r = (uint32_t)mul_signed<A>(x6, x1);
     return umin32(r, r + P);
   }
+  if (MODE & 128) return sbox7<true>(fp_add_alu(x, rc));
   return sbox7(fp_add(x, rc));
 }
 
@@ -132,7 +154,7 @@ __device__ __forceinline__ void partial_round(uint32_t (&c)[24], int r) {
     const uint32_t q = __umulhi(c[i], c_diag_q[i]);
     uint32_t r = c[i] * c_diag_n[i] - q * P;
     r = umin32(r, r - P);
-    c[i] = (MODE & 32) ? fp_add(r, sum) : fp_add_fma(r, sum);
+    c[i] = (MODE & 128) ? fp_add_alu(r, sum) : (MODE & 32) ? fp_add(r, sum) : fp_add_fma(r, sum);
   }
 }
 
@@ -149,7 +171,6 @@ __device__ __forceinline__ void p2_permute_m(uint32_t (&c)[24]) {
 #ifndef R0_P2_DEFAULT_MODE
 #define R0_P2_DEFAULT_MODE 32   // round-1 schedule: everything on the fma pipe except the partial round's "+ sum"
 #endif
-__device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) { p2_permute_m<R0_P2_DEFAULT_MODE>(c); }
 
 // out[row] = sponge over matrix[j*rows + row], j < cols (overwrite mode, zero-filled tail, empty input = one permute)
 template <int MODE>
@@ -190,24 +211,26 @@ __device__ __forceinline__ void load_pair(uint32_t (&c)[24], const uint32_t* __r
 }
 
 // one level: io[out_size + i] = H(io[in_size + 2i] || io[in_size + 2i + 1])
+template <int MODE>
 __global__ void __launch_bounds__(256) p2_hash_fold_kernel(uint32_t* io, size_t in_size, size_t out_size) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= out_size) return;
   uint32_t c[24];
   load_pair(c, io + (in_size + 2 * i) * 8);
-  p2_permute(c);
+  p2_permute_m<MODE>(c);
   uint4* o = reinterpret_cast<uint4*>(io + (out_size + i) * 8);
   o[0] = make_uint4(c[0], c[1], c[2], c[3]);
   o[1] = make_uint4(c[4], c[5], c[6], c[7]);
 }
 
 // generic pair hash with independent pointers (sppark_poseidon2_fold's signature): out[i] = H(in[2i] || in[2i+1])
+template <int MODE>
 __global__ void __launch_bounds__(256) p2_fold_pairs_kernel(uint32_t* out, const uint32_t* in, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t c[24];
   load_pair(c, in + 16 * i);
-  p2_permute(c);
+  p2_permute_m<MODE>(c);
   uint4* o = reinterpret_cast<uint4*>(out + i * 8);
   o[0] = make_uint4(c[0], c[1], c[2], c[3]);
   o[1] = make_uint4(c[4], c[5], c[6], c[7]);
@@ -215,6 +238,7 @@ __global__ void __launch_bounds__(256) p2_fold_pairs_kernel(uint32_t* out, const
 
 // Several levels per launch. A block takes 2*B consecutive nodes of the level of `in_size` nodes (B = blockDim.x),
 // and produces `levels` levels (B, B/2, ... nodes), each written to its heap position nodes[size + index].
+template <int MODE>
 __global__ void __launch_bounds__(256) p2_fold_tree_kernel(uint32_t* nodes, size_t in_size, int levels) {
   __shared__ uint32_t sh[256 * 8];
   const int B = blockDim.x;
@@ -245,7 +269,7 @@ __global__ void __launch_bounds__(256) p2_fold_tree_kernel(uint32_t* nodes, size
 #pragma unroll
         for (int i = 16; i < 24; i++) c[i] = 0;
       }
-      p2_permute(c);
+      p2_permute_m<MODE>(c);
       uint4* o = reinterpret_cast<uint4*>(nodes + (out_size + base + t) * 8);
       o[0] = make_uint4(c[0], c[1], c[2], c[3]);
       o[1] = make_uint4(c[4], c[5], c[6], c[7]);
@@ -268,21 +292,32 @@ void r0_poseidon2_init(Ctx* c) {
   for (int i = 0; i < 24; i++) dq[i] = (uint32_t)(((uint64_t)R0_P2_DIAG[i] << 32) / P);
   R0_CUDA(cudaMemcpyToSymbolAsync(c_diag_n, R0_P2_DIAG, sizeof(R0_P2_DIAG), 0, cudaMemcpyHostToDevice, c->stream));
   R0_CUDA(cudaMemcpyToSymbolAsync(c_diag_q, dq, sizeof(dq), 0, cudaMemcpyHostToDevice, c->stream));
-  const uint32_t one = 1;
+  const uint32_t one = 1, zero = 0;
   R0_CUDA(cudaMemcpyToSymbolAsync(c_one, &one, sizeof(one), 0, cudaMemcpyHostToDevice, c->stream));
+  R0_CUDA(cudaMemcpyToSymbolAsync(c_zero, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, c->stream));
   R0_CUDA(cudaStreamSynchronize(c->stream));
 }
+
+static int p2_mode() {
+  static const int mode = getenv("R0B200_P2_MODE") ? atoi(getenv("R0B200_P2_MODE")) : R0_P2_DEFAULT_MODE;
+  return mode;
+}
+// the fold kernels are compiled for the default schedule and the two reference points of the mode experiment
+#define P2_FOLD_DISPATCH(CALL)                         \
+  switch (p2_mode()) {                                 \
+    case 32: { constexpr int M = 32; CALL; } break;    \
+    case 128: { constexpr int M = 128; CALL; } break;  \
+    default: { constexpr int M = 192; CALL; } break;   \
+  }
 
 void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
   PhaseScope ph(c, "hash_rows", 4.0 * (double)rows * (double)cols + 32.0 * (double)rows);
   if (rows == 0) return;
   R0_CHECK(cols <= 0xffffffffull, "hash_rows: too many columns");
-  static const int mode = getenv("R0B200_P2_MODE") ? atoi(getenv("R0B200_P2_MODE")) : R0_P2_DEFAULT_MODE;
   const unsigned grid = (unsigned)((rows + 255) / 256);
 #define P2_ROWS(M) case M: p2_hash_rows_kernel<M><<<grid, 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
-  switch (mode) {
-    P2_ROWS(0) P2_ROWS(8) P2_ROWS(32) P2_ROWS(40) P2_ROWS(64) P2_ROWS(72) P2_ROWS(96) P2_ROWS(104) P2_ROWS(112) P2_ROWS(120)
-    P2_ROWS(100) P2_ROWS(108) P2_ROWS(124) P2_ROWS(127) P2_ROWS(63) P2_ROWS(98) P2_ROWS(106) P2_ROWS(122) P2_ROWS(116)
+  switch (p2_mode()) {
+    P2_ROWS(0) P2_ROWS(32) P2_ROWS(63) P2_ROWS(64) P2_ROWS(96) P2_ROWS(120) P2_ROWS(127) P2_ROWS(128) P2_ROWS(192)
     default: throw std::invalid_argument("R0B200_P2_MODE: mask not compiled in");
   }
 #undef P2_ROWS
@@ -294,7 +329,7 @@ void r0_p2_hash_fold(Ctx* c, uint32_t* io, size_t in_size, size_t out_size) {
   PhaseScope ph(c, "hash_fold", 96.0 * (double)out_size);
   R0_CHECK(in_size == 2 * out_size, "hash_fold: input_size must be 2 * output_size");
   if (out_size == 0) return;
-  p2_hash_fold_kernel<<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(io, in_size, out_size);
+  P2_FOLD_DISPATCH((p2_hash_fold_kernel<M><<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(io, in_size, out_size)));
   count_launch(c);
   R0_CUDA(cudaGetLastError());
 }
@@ -302,7 +337,7 @@ void r0_p2_hash_fold(Ctx* c, uint32_t* io, size_t in_size, size_t out_size) {
 void r0_p2_fold_pairs(Ctx* c, uint32_t* out, const uint32_t* in, size_t n) {
   PhaseScope ph(c, "hash_fold", 96.0 * (double)n);
   if (n == 0) return;
-  p2_fold_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(out, in, n);
+  P2_FOLD_DISPATCH((p2_fold_pairs_kernel<M><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(out, in, n)));
   count_launch(c);
   R0_CUDA(cudaGetLastError());
 }
@@ -315,7 +350,7 @@ void r0_p2_merkle_fold_all(Ctx* c, uint32_t* nodes, size_t leaves) {
   // tree (<= 2^13 nodes per level, latency-bound) is folded several levels per launch
   while (in_size > (size_t(1) << 14)) {
     size_t out_size = in_size / 2;
-    p2_hash_fold_kernel<<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(nodes, in_size, out_size);
+    P2_FOLD_DISPATCH((p2_hash_fold_kernel<M><<<(unsigned)((out_size + 255) / 256), 256, 0, c->stream>>>(nodes, in_size, out_size)));
     count_launch(c);
     in_size = out_size;
   }
@@ -325,7 +360,7 @@ void r0_p2_merkle_fold_all(Ctx* c, uint32_t* nodes, size_t leaves) {
     int levels = 1;
     while ((1 << levels) <= B) levels++;  // B = 2^j -> j + 1 levels (B, B/2, ..., 1)
     unsigned blocks = (unsigned)((out_size + B - 1) / B);
-    p2_fold_tree_kernel<<<blocks, B, 0, c->stream>>>(nodes, in_size, levels);
+    P2_FOLD_DISPATCH((p2_fold_tree_kernel<M><<<blocks, B, 0, c->stream>>>(nodes, in_size, levels)));
     count_launch(c);
     in_size >>= levels;
   }

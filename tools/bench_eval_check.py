@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--po2", type=int, default=18)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--tile-data", action="store_true", help="one random column repeated (fast host setup; timing only)")
     a = ap.parse_args()
     hal = B200Hal(0)
     n = 1 << a.po2
@@ -32,7 +33,11 @@ def main():
     def rand(k):
         return (rng.integers(0, P, size=k, dtype=np.uint64) * (2**32 % P) % P).astype(np.uint32)
 
-    accum, data = hal.copy_from_elem("accum", rand(103 * domain)), hal.copy_from_elem("data", rand(211 * domain))
+    if a.tile_data:
+        col = rand(domain)
+        accum, data = hal.copy_from_elem("accum", np.tile(col, 103)), hal.copy_from_elem("data", np.tile(col[::-1], 211))
+    else:
+        accum, data = hal.copy_from_elem("accum", rand(103 * domain)), hal.copy_from_elem("data", rand(211 * domain))
     code = hal.alloc_elem_init("code", domain, 0)
     mix, out = hal.copy_from_elem("mix", rand(36)), hal.copy_from_elem("out", rand(90))
     check = hal.alloc_elem("check", 4 * domain)

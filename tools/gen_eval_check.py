@@ -629,6 +629,26 @@ def schedule_scalars(S, outs):
 
 
 # ------------------------------------------------------------------------------------------------ PTX emission
+_TUNE = None
+
+
+def part_opt(part, key, default):
+    """generator option for one part kernel: the measured per-part choice (risc0_b200/circuits/<circuit>.tune.json,
+    written by tools/autotune_eval_check.py) unless EVAL_IGNORE_TUNE=1, else the environment, else the default.
+    Every option only changes the ORDER / placement of exact field operations: results are bit-identical."""
+    global _TUNE
+    if _TUNE is None:
+        _TUNE = {}
+        if os.environ.get("EVAL_IGNORE_TUNE") != "1":
+            import glob
+            for f in glob.glob(os.path.join(ROOT, "risc0_b200", "circuits", "*.tune.json")):
+                _TUNE.update(json.load(open(f)).get("gen", {}))
+    v = _TUNE.get(part, {}).get(key)
+    if v is None:
+        v = os.environ.get(key, default)
+    return v
+
+
 class Ptx:
     def __init__(self, S, name, lay):
         self.S, self.name, self.lay = S, name, lay
@@ -637,12 +657,14 @@ class Ptx:
         self.nw = 0   # u64 temporaries
         self.nl = 0   # tap load registers
         self.pos = 0
-        self.remat = int(os.environ.get("EVAL_REMAT_DIST", "400"))   # re-load / recompute instead of keeping alive
-        self.remat_cost = int(os.environ.get("EVAL_REMAT_COST", "8"))
-        self.split = int(os.environ.get("EVAL_SPLIT", "1600"))
+        self.remat = int(part_opt(name, "EVAL_REMAT_DIST", "400"))   # re-load / recompute instead of keeping alive
+        self.remat_cost = int(part_opt(name, "EVAL_REMAT_COST", "8"))
+        self.split = int(part_opt(name, "EVAL_SPLIT", "1600"))
         self.last_fence = 0
         self.use_bar = os.environ.get("EVAL_BAR", "0") == "1"
         self.first_wide = os.environ.get("EVAL_FIRST_WIDE", "1") == "1"
+        self.mshift = os.environ.get("EVAL_MSHIFT", "0") == "1"
+        self.pin_adds = os.environ.get("EVAL_PIN", "0") == "1"
         self.bases = {}
 
     def t(self):
@@ -712,13 +734,31 @@ class Ptx:
             self.emit("mad.lo.cc.u32 %s, %s, %s, %s;" % (lo, a, b, lo))
             self.emit("madc.hi.u32 %s, %s, %s, %s;" % (hi, a, b, hi))
 
+    def pin(self, r):
+        """r += 0 with a zero ptxas cannot see through: the preceding two-input add / sub becomes a three-input IADD3,
+        which ptxas cannot re-issue as IMAD.IADD on the fma pipe (it balances instruction COUNTS between the integer
+        pipes and does not know that IMAD.WIDE / IMAD.HI hold the fma pipe twice as long as an IMAD)"""
+        if self.pin_adds:
+            self.emit("add.u32 %s, %s, %%zr;" % (r, r))
+
     def mont_finish(self, dst, lo, hi):
         # subtractive Montgomery reduction (csrc/fp.cuh mont_reduce): m = lo * P^-1; r = hi - hi(m * P) in (-P, P);
         # canonical = min.u32(r, r + P). No carry chain, 4 instructions.
         m, h, r, r2 = self.t(), self.t(), self.t(), self.t()
-        self.emit("mul.lo.u32 %s, %s, %d;" % (m, lo, PINV))
+        if self.mshift:
+            # m = lo * P^-1 with P^-1 = 1 + 2^27 + 2^31 as two shifts and one three-input add on the alu pipe (which is
+            # half idle in these kernels) instead of an IMAD on the saturated fma pipe. The shift amounts are opaque
+            # registers (27 / 31 + (domain & 1)): with immediates ptxas turns the shift-adds back into IMADs.
+            a, b, c = self.t(), self.t(), self.t()
+            self.emit("shl.b32 %s, %s, %%sh27;" % (a, lo))
+            self.emit("shl.b32 %s, %s, %%sh31;" % (b, lo))
+            self.emit("add.u32 %s, %s, %s;" % (c, lo, a))
+            self.emit("add.u32 %s, %s, %s;" % (m, c, b))
+        else:
+            self.emit("mul.lo.u32 %s, %s, %d;" % (m, lo, PINV))
         self.emit("mul.hi.u32 %s, %s, %d;" % (h, m, P))
         self.emit("sub.u32 %s, %s, %s;" % (r, hi, h))
+        self.pin(r)
         self.emit("add.u32 %s, %s, %d;" % (r2, r, P))
         self.emit("min.u32 %s, %s, %s;" % (dst, r, r2))
 
@@ -740,9 +780,11 @@ class Ptx:
             t1, t2 = self.t(), self.t()
             if o == "+":
                 self.emit("add.u32 %s, %s, %s;" % (t1, a, b))
+                self.pin(t1)
                 self.emit("add.u32 %s, %s, %d;" % (t2, t1, (1 << 32) - P))
             else:
                 self.emit("sub.u32 %s, %s, %s;" % (t1, a, b))
+                self.pin(t1)
                 self.emit("add.u32 %s, %s, %d;" % (t2, t1, P))
             self.emit("min.u32 %s, %s, %s;" % (dst, t1, t2))
         elif o == "n":
@@ -843,6 +885,16 @@ class Ptx:
                     o = self.w()
                     self.emit("ld.param.u64 %s, [p_cst+%d];" % (o, self.lay.coloff + 8 * k[2]))
                     self.emit("add.u64 %s, %s, %s;" % (a, base, o))
+                elif self.pin_adds:
+                    # explicit uniform product + carry-chained add: with every other add pinned to the alu pipe ptxas
+                    # would otherwise fold this into a per-thread IMAD.WIDE (4 fma-pipe cycles per tap load)
+                    o, ol, oh, bl, bh = self.w(), self.t(), self.t(), self.t(), self.t()
+                    self.emit("mul.wide.u32 %s, %%stride, %d;" % (o, k[2]))
+                    self.emit("mov.b64 {%s, %s}, %s;" % (ol, oh, o))
+                    self.emit("mov.b64 {%s, %s}, %s;" % (bl, bh, base))
+                    self.emit("add.cc.u32 %s, %s, %s;" % (ol, ol, bl))
+                    self.emit("addc.u32 %s, %s, %s;" % (oh, oh, bh))
+                    self.emit("mov.b64 %s, {%s, %s};" % (a, ol, oh))
                 else:
                     self.emit("mad.wide.u32 %s, %%stride, %d, %s;" % (a, k[2], base))
                 self.emit("ld.global.nc.u32 %s, [%s];" % (reg, a))
@@ -870,7 +922,7 @@ class Ptx:
                 keyed.setdefault(key, []).append((d, a, b))
         acc = {d: None for d in dots}      # (lo, hi) register pair once the first product has been issued
         bound = {d: 0 for d in dots}
-        if os.environ.get("EVAL_ORDER", "program") == "weight":
+        if part_opt(self.name, "EVAL_ORDER", "program") == "weight":
             order = sorted(keyed, key=lambda key: -max([self.weight[x] for x in key] or [0]))
         else:
             order = list(keyed)    # first-appearance order = the constraint system's own order
@@ -921,7 +973,7 @@ class Ptx:
         L.append("    .reg .u32 %%c<%d>;" % (self.ncopy + 2))
         L.append("    .reg .u64 %%w<%d>;" % (self.nw + 40))
         L.append("    .reg .u32 %i, %i0, %domain, %mask, %first, %stride, %bdim, %bidx, %lane;")
-        L.append("    .reg .u32 %o<8>, %q<8>, %iy<6>, %res<4>;")
+        L.append("    .reg .u32 %o<8>, %q<8>, %iy<6>, %res<4>, %sh27, %sh31, %zr;")
         L.append("    .reg .u64 %check, %accum, %code, %data, %oaddr<4>, %off;")
         for (buf, back), base in sorted(self.bases.items()):
             L.append("    .reg .u64 %s;" % base)
@@ -948,6 +1000,10 @@ class Ptx:
         L.append("    add.u32 %mask, %domain, -1;")
         L.append("    shl.b32 %stride, %domain, 2;")
         L.append("    setp.eq.u32 %p0, %domain, 3;")
+        if self.mshift or self.pin_adds:
+            L.append("    and.b32 %zr, %domain, 1;")     # 0 (the domain is a power of two >= 4), unknown to ptxas
+            L.append("    add.u32 %sh31, %zr, 31;")
+            L.append("    add.u32 %sh27, %zr, 27;")
         n = 0
         for (buf, back), base in sorted(self.bases.items()):
             # element index (i - 4*back) & mask, byte address = buf + 4 * index
@@ -1064,6 +1120,9 @@ LAUNCHER = r"""// GENERATED by tools/gen_eval_check.py - do not edit. Circuit %(
 // (constant bank): poly_mix powers, their -11 multiples, globals, mix values and the 4 divisor inverses.
 #include <algorithm>
 #include <mutex>
+#include <string>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../ctx.h"
@@ -1107,7 +1166,17 @@ void load_kernels() {
   const char* names[kParts] = {%(names)s};
   for (int j = 0; j < kParts; j++) {
     cudaLibrary_t lib;
-    cudaError_t e = cudaLibraryLoadData(&lib, images[j], nullptr, nullptr, 0, nullptr, nullptr, 0);
+    // experiment hook (tools/autotune_eval_check.py): a cubin of the same name in $R0B200_CUBIN_DIR replaces the
+    // embedded image, so differently assembled parts can be timed without building a library per variant
+    cudaError_t e = cudaErrorFileNotFound;
+    if (const char* dir = getenv("R0B200_CUBIN_DIR")) {
+      const std::string path = std::string(dir) + "/" + names[j] + ".cubin";
+      if (FILE* f = fopen(path.c_str(), "rb")) {
+        fclose(f);
+        e = cudaLibraryLoadFromFile(&lib, path.c_str(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+      }
+    }
+    if (e == cudaErrorFileNotFound) e = cudaLibraryLoadData(&lib, images[j], nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&g_kernels[j], lib, names[j]);
     if (e != cudaSuccess) {
       g_load_error = std::string("loading ") + names[j] + ": " + cudaGetErrorString(e);
@@ -1262,7 +1331,7 @@ def main():
             uses[k[1]] += 1
             uses[k[2]] += 1
     parts = partition(dag, uses, nparts)
-    gen_dir = os.path.join(ROOT, "risc0_b200", "csrc", "gen")
+    gen_dir = os.environ.get("EVAL_OUT_DIR") or os.path.join(ROOT, "risc0_b200", "csrc", "gen")
     os.makedirs(gen_dir, exist_ok=True)
     for f in os.listdir(gen_dir):
         if f.startswith("eval_check_%s" % name):
@@ -1298,8 +1367,9 @@ def main():
     with open(os.path.join(gen_dir, "eval_check_%s.cu" % name), "w") as f:
         f.write(LAUNCHER % params)
     # per-point operation counts of the emitted kernels (bench.py's INT32 roofline reads them)
-    with open(os.path.join(ROOT, "risc0_b200", "circuits", name + ".stats.json"), "w") as f:
-        json.dump(stats, f, indent=1)
+    if not os.environ.get("EVAL_OUT_DIR"):
+        with open(os.path.join(ROOT, "risc0_b200", "circuits", name + ".stats.json"), "w") as f:
+            json.dump(stats, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -9,11 +9,14 @@ constexpr int CH = 8;  // independent chains per thread
 
 template <int OP>
 __global__ void k(uint32_t* out, uint32_t a0, uint32_t b0) {
-  uint32_t x[CH], y[CH];
+  uint32_t x[CH], y[CH], z[CH], w[CH], v[CH];
 #pragma unroll
   for (int i = 0; i < CH; i++) {
     x[i] = a0 + threadIdx.x + i;
     y[i] = b0 ^ (threadIdx.x * 7 + i);
+    z[i] = x[i] * 3 + 1;
+    w[i] = y[i] * 5 + 2;
+    v[i] = y[i] * 9 + 4;
   }
   for (int it = 0; it < ITERS; it++) {
 #pragma unroll
@@ -70,6 +73,89 @@ __global__ void k(uint32_t* out, uint32_t a0, uint32_t b0) {
         uint32_t r = (uint32_t)(t >> 32) - h;
         uint32_t r2 = r + 0x78000001u;
         x[i] = r < r2 ? r : r2;
+      } else if (OP == 13) {  // IMAD + IADD3
+        asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(x[i]) : "r"(y[i]));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a0));
+      } else if (OP == 14) {  // IMAD + LEA
+        asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(x[i]) : "r"(y[i]));
+        y[i] = (y[i] << 5) + a0;
+      } else if (OP == 15) {  // IMAD + IADD3 + VIADDMNMX
+        asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(x[i]) : "r"(y[i]));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a0));
+        uint32_t t;
+        asm volatile("add.u32 %0, %1, 0x87ffffff;" : "=r"(t) : "r"(y[i]));
+        asm volatile("min.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(t));
+      } else if (OP == 16) {  // IMAD + 2 IADD3
+        asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(x[i]) : "r"(y[i]));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(z[i]) : "r"(b0));
+      } else if (OP == 17) {  // IMAD.HI + 3 IADD3
+        asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(b0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(z[i]) : "r"(b0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(w[i]) : "r"(b0));
+      } else if (OP == 18) {  // Montgomery product, m = lo + ((17 lo) << 27) as two LEA
+        uint64_t t = (uint64_t)x[i] * y[i];
+        uint32_t lo = (uint32_t)t, t17, m;
+        asm volatile("shl.b32 %0, %1, 4;\n\tadd.u32 %0, %0, %1;" : "=&r"(t17) : "r"(lo));
+        asm volatile("shl.b32 %0, %1, 27;\n\tadd.u32 %0, %0, %2;" : "=&r"(m) : "r"(t17), "r"(lo));
+        uint32_t h = __umulhi(m, 0x78000001u);
+        uint32_t r = (uint32_t)(t >> 32) - h;
+        uint32_t r2 = r + 0x78000001u;
+        x[i] = r < r2 ? r : r2;
+      } else if (OP == 19) {  // IMAD + SHF (funnel shift)
+        asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(x[i]) : "r"(y[i]));
+        asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(z[i]) : "r"(a0));
+      } else if (OP == 20) {  // IMAD + LOP3
+        asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(x[i]) : "r"(y[i]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"(a0), "r"(w[i]));
+      } else if (OP == 21) {  // LEA alone
+        y[i] = (y[i] << 5) + a0;
+        asm volatile("" : "+r"(y[i]));
+      } else if (OP == 22) {  // SHF alone
+        asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(z[i]) : "r"(a0));
+      } else if (OP == 23) {  // LOP3 alone (3-input xor)
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"(a0), "r"(w[i]));
+      } else if (OP == 24) {  // VIMNMX alone
+        asm volatile("min.u32 %0, %0, %1;" : "+r"(z[i]) : "r"(w[i]));
+        asm volatile("max.u32 %0, %0, %1;" : "+r"(w[i]) : "r"(a0));
+      } else if (OP == 25) {  // IMAD.WIDE + 2 VIADDMNMX
+        uint64_t t;
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(x[i]), "r"(y[i]));
+        x[i] = (uint32_t)t ^ (uint32_t)(t >> 32);
+        uint32_t u;
+        asm volatile("add.u32 %0, %1, 0x87ffffff;" : "=r"(u) : "r"(z[i]));
+        asm volatile("min.u32 %0, %0, %1;" : "+r"(z[i]) : "r"(u));
+        asm volatile("add.u32 %0, %1, 0x87ffffff;" : "=r"(u) : "r"(w[i]));
+        asm volatile("min.u32 %0, %0, %1;" : "+r"(w[i]) : "r"(u));
+      } else if (OP == 26) {  // IMAD.HI + 2 VIADDMNMX + 2 IADD3 : 4 fma cycles, 4 alu-only cycles, 2 flexible
+        asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(b0));
+        uint32_t u;
+        asm volatile("add.u32 %0, %1, 0x87ffffff;" : "=r"(u) : "r"(z[i]));
+        asm volatile("min.u32 %0, %0, %1;" : "+r"(z[i]) : "r"(u));
+        asm volatile("add.u32 %0, %1, 0x87ffffff;" : "=r"(u) : "r"(w[i]));
+        asm volatile("min.u32 %0, %0, %1;" : "+r"(w[i]) : "r"(u));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(v[i]) : "r"(b0));
+      } else if (OP == 27) {  // IMAD.HI + 2 VIADDMNMX (4 fma cycles, 4 alu cycles)
+        asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(b0));
+        uint32_t u;
+        asm volatile("add.u32 %0, %1, 0x87ffffff;" : "=r"(u) : "r"(z[i]));
+        asm volatile("min.u32 %0, %0, %1;" : "+r"(z[i]) : "r"(u));
+        asm volatile("add.u32 %0, %1, 0x87ffffff;" : "=r"(u) : "r"(w[i]));
+        asm volatile("min.u32 %0, %0, %1;" : "+r"(w[i]) : "r"(u));
+      } else if (OP == 28) {  // IMAD.HI + 4 IADD3
+        asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(b0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(z[i]) : "r"(b0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(w[i]) : "r"(b0));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(v[i]) : "r"(a0));
+      } else if (OP == 29) {  // 64-bit add (IADD3 + IADD3.X carry pair)
+        asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(a0), "r"(b0));
+      } else if (OP == 30) {  // ISETP + SEL
+        uint32_t u = z[i] + a0;
+        z[i] = (u >= 0x78000001u) ? u - 0x78000001u : u;
+        asm volatile("" : "+r"(z[i]));
       } else if (OP == 10) {  // SHF / shl alone
         asm volatile("shl.b32 %0, %0, 3;" : "+r"(x[i]));
         asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
@@ -81,7 +167,7 @@ __global__ void k(uint32_t* out, uint32_t a0, uint32_t b0) {
   }
   uint32_t s = 0;
 #pragma unroll
-  for (int i = 0; i < CH; i++) s ^= x[i] ^ y[i];
+  for (int i = 0; i < CH; i++) s ^= x[i] ^ y[i] ^ z[i] ^ w[i] ^ v[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -123,6 +209,24 @@ int main() {
   run<8>("Montgomery product (5 instr)", 1, out, p.multiProcessorCount, ghz);
   run<9>("Montgomery product, m by shift-add", 1, out, p.multiProcessorCount, ghz);
   run<12>("Montgomery product, m by LEA+SHF+LOP3", 1, out, p.multiProcessorCount, ghz);
+  run<13>("IMAD + IADD3", 2, out, p.multiProcessorCount, ghz);
+  run<14>("IMAD + LEA", 2, out, p.multiProcessorCount, ghz);
+  run<15>("IMAD + IADD3 + VIADDMNMX", 3, out, p.multiProcessorCount, ghz);
+  run<16>("IMAD + 2 IADD3", 3, out, p.multiProcessorCount, ghz);
+  run<17>("IMAD.HI + 3 IADD3", 4, out, p.multiProcessorCount, ghz);
+  run<28>("IMAD.HI + 4 IADD3", 5, out, p.multiProcessorCount, ghz);
+  run<27>("IMAD.HI + 2 VIADDMNMX", 3, out, p.multiProcessorCount, ghz);
+  run<26>("IMAD.HI + 2 VIADDMNMX + 2 IADD3", 5, out, p.multiProcessorCount, ghz);
+  run<25>("IMAD.WIDE(+LOP3) + 2 VIADDMNMX", 4, out, p.multiProcessorCount, ghz);
+  run<18>("Montgomery product, m by two LEA", 1, out, p.multiProcessorCount, ghz);
+  run<19>("IMAD + SHF", 2, out, p.multiProcessorCount, ghz);
+  run<20>("IMAD + LOP3", 2, out, p.multiProcessorCount, ghz);
+  run<21>("LEA", 1, out, p.multiProcessorCount, ghz);
+  run<22>("SHF", 1, out, p.multiProcessorCount, ghz);
+  run<23>("LOP3 (3-input)", 1, out, p.multiProcessorCount, ghz);
+  run<24>("VIMNMX (min + max)", 2, out, p.multiProcessorCount, ghz);
+  run<29>("IADD3 + IADD3.X (64-bit add)", 2, out, p.multiProcessorCount, ghz);
+  run<30>("add + ISETP + SEL-style reduce", 1, out, p.multiProcessorCount, ghz);
   run<10>("shl + add", 2, out, p.multiProcessorCount, ghz);
   run<11>("xor + and (LOP3)", 2, out, p.multiProcessorCount, ghz);
   return 0;
