@@ -10,7 +10,7 @@ namespace {   // internal linkage: both step translation units instantiate the s
 }  // namespace
 
 #ifndef WG_MIN_BLOCKS
-#define WG_MIN_BLOCKS 1
+#define WG_MIN_BLOCKS 8   // measured at po2 = 20 (tools/witgen_variants.sh): 1 -> 4.15 ms, 6 -> 3.62, 8 -> 3.06, 10 -> 3.29
 #endif
 __global__ void __launch_bounds__(128, WG_MIN_BLOCKS) k_step_accum(const WShared* s, const uint32_t* order, uint32_t count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

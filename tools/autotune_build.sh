@@ -9,13 +9,14 @@ python - <<'PY'
 import concurrent.futures as cf, glob, json, os, subprocess, sys
 sys.path.insert(0, ".")
 from risc0_b200 import build as b
-V = json.load(open("tools/autotune_variants.json"))
+V = json.load(open(os.environ.get("AT_VARIANTS", "tools/autotune_variants.json")))
+PFX = V.get("prefix", "g")
 variants = []   # (name, gen env, flags)
 for gi, g in enumerate(V["gen"]):
     for fi, f in enumerate(V["flags"]):
-        variants.append(("g%df%d" % (gi, fi), g, f))
+        variants.append(("%s%df%d" % (PFX, gi, fi), g, f))
 for fi, f in enumerate(V["extra_default_gen_flags"]):
-    variants.append(("g0x%d" % fi, {}, f))
+    variants.append(("%s0x%d" % (PFX, fi), {}, f))
 gens = {}
 for gi, g in enumerate(V["gen"]):
     d = "/tmp/at_gen/g%d" % gi
@@ -24,10 +25,18 @@ for gi, g in enumerate(V["gen"]):
     gens[gi] = (d, subprocess.Popen([sys.executable, "tools/gen_eval_check.py", "rv32im", "--from-ir"], env=env, stdout=subprocess.DEVNULL))
 for d, p in gens.values():
     assert p.wait() == 0
+    assert len(glob.glob(d + "/*.ptx")) == 36, d
 jobs = []
 with cf.ThreadPoolExecutor(max_workers=os.cpu_count()) as ex:
     for name, g, f in variants:
-        gi = V["gen"].index(g)
+        gi = V["gen"].index(g) if g in V["gen"] else None
+        if gi is None:      # default generator options (extra flag sets): generate once
+            gi = "d"
+            if gi not in gens:
+                d = "/tmp/at_gen/gd"
+                os.makedirs(d, exist_ok=True)
+                subprocess.check_call([sys.executable, "tools/gen_eval_check.py", "rv32im", "--from-ir"], env=dict(os.environ, EVAL_IGNORE_TUNE="1", EVAL_OUT_DIR=d), stdout=subprocess.DEVNULL)
+                gens[gi] = (d, None)
         out = os.path.join("risc0_b200", "lib", "cubins_at", name)
         os.makedirs(out, exist_ok=True)
         for ptx in sorted(glob.glob(gens[gi][0] + "/eval_check_rv32im_p*.ptx")):

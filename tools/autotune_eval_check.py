@@ -43,6 +43,20 @@ def main():
         per_part[p] = dict(default_ms=t_base, best_ms=t_best, best=best, chosen=chosen,
                            top5={v: by_var[v][p] for v in sorted(by_var, key=lambda v: by_var[v][p])[:5]})
         print("%-16s default %.3f  best %.3f  %-6s gen %s flags %s" % (p, t_base, t_best, chosen, variants[best]["gen"], " ".join(variants[best]["flags"])))
+    if "--update" in sys.argv:      # a later round: `default` in this log is the build tuned so far; keep its entries
+        path = os.path.join(ROOT, "risc0_b200", "circuits", "rv32im.tune.json")
+        old = json.load(open(path))
+        for name in list(old["flags"]):
+            if name not in flags:
+                flags[name] = old["flags"][name]
+                if name in old["gen"]:
+                    gen[name] = old["gen"][name]
+        for p_, e in old["per_part"].items():
+            if per_part[p_]["chosen"] == "default":
+                per_part[p_] = dict(e, tuned_ms=per_part[p_]["default_ms"])
+            else:
+                per_part[p_]["default_ms"] = e["default_ms"]
+        base = dict(base, eval_check=old["baseline_ms"])
     out = dict(circuit="rv32im", measured="po2 = %d on a B200, per-part CUDA-event times (tools/autotune_run.sh)" % base["po2"],
                baseline_ms=base["eval_check"], predicted_ms=round(total, 3), gen=gen, flags=flags, per_part=per_part)
     with open(os.path.join(ROOT, "risc0_b200", "circuits", "rv32im.tune.json"), "w") as f:

@@ -1,5 +1,5 @@
 # on the GPU box: per-part eval_check times of every variant directory -> gpurun_out/r2_autotune.log
-out=gpurun_out/r2_autotune.log
+out=gpurun_out/${AT_LOG:-r2_autotune.log}
 rm -f $out
 python tools/bench_eval_check.py --po2 ${PO2:-20} --iters 3 --tile-data >> $out 2>&1
 for d in risc0_b200/lib/cubins_at/*/; do

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--po2", type=int, default=18)
     ap.add_argument("--segments", type=int, default=5)
     ap.add_argument("--gpus", type=int, default=2)
+    ap.add_argument("--devices", default="", help="explicit device ordinal per worker, e.g. 0,0 = two workers sharing GPU 0")
     ap.add_argument("--check", action="store_true", help="re-prove every segment on device 0 alone and compare seals")
     ap.add_argument("--precomputed", action="store_true",
                     help="run preflight before the timed region (the reference's Rust preflight is ~100x faster than this "
@@ -38,14 +39,15 @@ def main():
     rand_z = (11, 22, 33, 44)
     work = [PF.PreflightResults(s_, rand_z) for s_ in segs] if a.precomputed else segs
     # warm every device once (module load, pool growth) so the timed run is steady state
-    sched = b200_scheduler(list(range(a.gpus)), rand_z=rand_z, cpu_workers=2)
-    sched.run(work[:a.gpus])
-    sched = b200_scheduler(list(range(a.gpus)), rand_z=rand_z, cpu_workers=2)
+    devices = [int(x) for x in a.devices.split(",")] if a.devices else list(range(a.gpus))
+    sched = b200_scheduler(devices, rand_z=rand_z, cpu_workers=2)
+    sched.run(work[:len(devices)])
+    sched = b200_scheduler(devices, rand_z=rand_z, cpu_workers=2)
     t0 = time.perf_counter()
     res = sched.run(work)
     wall = time.perf_counter() - t0
     cycles = sum(s.suspend_cycle for s in segs)
-    out = {"po2": a.po2, "segments": len(segs), "gpus": a.gpus, "wall_s": round(wall, 3), "user_cycles": cycles,
+    out = {"po2": a.po2, "segments": len(segs), "gpus": a.gpus, "devices": devices, "wall_s": round(wall, 3), "user_cycles": cycles,
            "cycles_per_s": round(cycles / wall), "per_device": {str(w.device): w.proved for w in sched.workers},
            "device_busy_s": {str(w.device): round(w.busy_s, 3) for w in sched.workers},
            "preflight_s": [round(r.t_preflight, 2) for r in res], "prove_s": [round(r.t_prove, 3) for r in res],

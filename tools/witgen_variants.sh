@@ -1,3 +1,4 @@
+# on the GPU box: witgen / accum phase times for the default library and the variants named on the command line
 out=gpurun_out/r2_witgen_variants.log
 rm -f $out
 python tools/bench_witgen.py --po2 20 >> $out 2>&1
