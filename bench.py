@@ -284,6 +284,8 @@ def main():
     ap.add_argument("--cpu-po2", type=int, default=16, dest="cpu_po2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs 3-5 short runs (po2=22, recursion, sweeps)")
+    ap.add_argument("--in-flight", type=int, default=2, dest="in_flight",
+                    help="segments proved concurrently per GPU (host threads, one context each); 1 = strictly one at a time")
     ap.add_argument("--hash", default="poseidon2", choices=["poseidon2", "sha-256"],
                     help="hash suite (the reference's default for rv32im segments is poseidon2)")
     args = ap.parse_args()
@@ -322,42 +324,106 @@ def main():
     def max_over_ranks(x):
         return shard.max_over_ranks(x, device="cuda")
 
+    # ---- W segments in flight per GPU: W host threads, each with its own context (stream, copy stream, memory pool)
+    # and SegmentProver, taking steps from a shared counter. While one segment sits in a latency-bound stretch (witgen,
+    # the narrow top of a Merkle tree, the FRI tail, a host round trip for the transcript) the other's kernels fill the
+    # SMs: measured +4 % segments/s at W = 2 over W = 1 at po2 = 20 (tools/bench_inflight.py). Seals are identical.
+    W = max(1, args.in_flight)
+    hals = [hal] + [B200Hal(local_rank, args.hash) for _ in range(W - 1)]
+    provers = [prover] + [SegmentProver(h) for h in hals[1:]]
+
+    def sync_all():
+        for h in hals:
+            h.sync()
+
+    def run_steps(k, step_fn):
+        """k steps over the W workers; step_fn(worker, take) proves until take() returns None. Returns the last seal."""
+        lock, nxt, last, errs = threading.Lock(), [0], [None] * W, []
+
+        def take():
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+                return i if i < k else None
+
+        def body(w):
+            try:
+                last[w] = step_fn(w, take)
+            except BaseException as e:   # noqa: BLE001
+                errs.append(e)
+
+        if W == 1:
+            body(0)
+        else:
+            th = [threading.Thread(target=body, args=(w,)) for w in range(W)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        if errs:
+            raise errs[0]
+        return next(x for x in last if x is not None)
+
     # ---- device-resident arm: the segment (trace, injector, globals) is in HBM; each step is one whole prove_core
-    resident = prover.upload_segment(pf)
-    hal.sync()
+    resident = [p.upload_segment(pf) for p in provers]
+    sync_all()
+
+    def resident_worker(w, take):
+        out = None
+        while take() is not None:
+            out = provers[w].prove_segment(resident[w], free=False)[0]
+        return out
+
+    # one-in-flight pass with per-phase events: the kernel times behind `roofline` / `phase_ms_per_step` (with two
+    # contexts interleaving on the GPU a phase's event pair would also span the other context's kernels)
     for _ in range(args.warmup):
-        seal = prover.prove_segment(resident, free=False)[0]
+        seal = prover.prove_segment(resident[0], free=False)[0]
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = hal.launch_count()
     hal.profile_begin()
     hal.timer_start()
     for _ in range(args.steps):
-        seal = prover.prove_segment(resident, free=False)[0]
-    ms = hal.timer_stop()
+        seal = prover.prove_segment(resident[0], free=False)[0]
+    ms_one = hal.timer_stop()
     phases = hal.profile_end()
-    launches = hal.launch_count() - launches0
+    ms_one = max_over_ranks(ms_one)
+
+    run_steps(max(args.warmup, W), resident_worker)
+    sync_all()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sum(h.launch_count() for h in hals)
+    hal.timer_start()
+    seal = run_steps(args.steps, resident_worker)
+    sync_all()
+    ms = hal.timer_stop()
+    launches = sum(h.launch_count() for h in hals) - launches0
     barrier()
     ms = max_over_ranks(ms)
-    prover.free_segment(resident)
+    for p, r in zip(provers, resident):
+        p.free_segment(r)
 
-    # ---- end-to-end arm: the segment starts in pinned host memory every step. Depth-2 pipeline as the reference's
-    # worker queues do: the upload of step s+1 is enqueued on the copy stream before step s is proved. Every step's H2D
-    # copy and seal D2H are inside the timed region; nothing about a step exists on the device before its own upload.
-    def e2e_steps(k):
-        up = prover.upload_segment(pf)
-        out = None
-        for s_ in range(k):
-            nxt = prover.upload_segment(pf) if s_ + 1 < k else None
-            out = prover.prove_segment(up)[0]
-            up = nxt
+    # ---- end-to-end arm: the segment starts in pinned host memory every step. Depth-2 pipeline per worker as the
+    # reference's worker queues do: the upload of a worker's next step is enqueued on its copy stream before the current
+    # one is proved. Every step's H2D copy and seal D2H are inside the timed region; nothing about a step exists on the
+    # device before its own upload.
+    def e2e_worker(w, take):
+        p, out = provers[w], None
+        i = take()
+        up = p.upload_segment(pf) if i is not None else None
+        while i is not None:
+            j = take()
+            nxt_up = p.upload_segment(pf) if j is not None else None
+            out = p.prove_segment(up)[0]
+            i, up = j, nxt_up
         return out
 
-    e2e_steps(min(args.warmup, 2))
+    run_steps(max(min(args.warmup, 2), W) * 2, e2e_worker)
+    sync_all()
     barrier()
     hal.timer_start()
-    seal = e2e_steps(args.steps)
+    seal = run_steps(args.steps, e2e_worker)
+    sync_all()
     e2e_ms = hal.timer_stop()
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
@@ -404,7 +470,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "launches": nlaunch, "avg_launch_ms": t["ms"] / max(nlaunch, 1),
-                "share_of_step": t["ms"] / ms,
+                "share_of_step": t["ms"] / ms_one,
                 "note": "achieved = algorithmic bytes ((4*315+16) B per domain point for eval_check, 4*cols+32 B per row for "
                         "hash_rows) / summed device time of the family. Both are INT32-bound, not HBM-bound (Poseidon2: 1356 "
                         "modmul per permutation; eval_check: ~270 k instructions per point). See DESIGN.md 3.3/3.4 and profiles/."}
@@ -458,19 +524,24 @@ def main():
                 "config": {"workload": "rv32im segment po2=%d full prove_core from a preflight trace (witgen + accum + NTT + Poseidon2 "
                                        "Merkle + eval_check + DEEP + FRI), loop guest" % po2,
                            "guest": "execute/testutil.rs kernel::simple_loop, first (full) segment; real, constraint-satisfying witness",
-                           "segments_per_step_per_gpu": 1, "user_cycles_per_segment": cycles, "total_cycles_per_segment": n,
+                           "segments_per_step_per_gpu": 1, "segments_in_flight_per_gpu": W,
+                           "user_cycles_per_segment": cycles, "total_cycles_per_segment": n,
                            "hash": args.hash, "l2": "inputs (0.9 GB data witness, 5.5 GB evaluations) exceed the 126 MB L2",
                            "parallelism": "segments sharded one per GPU, no collective",
                            "setup_s": round(t_setup, 1)},
                 "e2e": {"value": e2e_value, "unit": "cycles/s", "h2d_bytes_per_step": int(pf.h2d_bytes), "d2h_bytes_per_step": int(seal.nbytes) + 360,
                         "ms_per_step": e2e_ms / args.steps,
                         "pipeline": "each step uploads its own segment (preflight trace + injector + globals) from pinned host memory "
-                                    "with r0b200_segment_upload on the copy stream, one step ahead of the proof (depth 2), and reads the "
-                                    "seal + globals back; the witness matrices never exist on the host"},
+                                    "with r0b200_segment_upload on its worker's copy stream, one step ahead of the proof (depth 2 per "
+                                    "worker, %d workers per GPU), and reads the seal + globals back; the witness matrices never exist "
+                                    "on the host" % W},
                 "gpu_launches": int(launches), "roofline": roofline, "int32_roofline": int32, "cpu_baseline": cpu_baseline,
+                "ms_per_step_one_in_flight": ms_one / args.steps,
                 "phase_ms_per_step": phase_ms, "phase_alg_GBps": phase_gbs, "clocks": sampler.result(),
-                "seal_words": int(len(seal)), "peak_device_bytes": hal.bytes_peak(), "configs": extras}
+                "seal_words": int(len(seal)), "peak_device_bytes": sum(h.bytes_peak() for h in hals), "configs": extras}
         emit(line)
+    for h in hals[1:]:
+        h.close()
     hal.close()
     if world > 1:
         dist.destroy_process_group()

@@ -208,7 +208,7 @@ def build(force=False, verbose=False, jobs=None):
                 raise RuntimeError("embedding cubins failed:\n%s" % r.stderr)
             todo.append((embed_s, embed_o))
         objs.append(embed_o)
-    if todo or not os.path.exists(LIB):
+    if todo or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

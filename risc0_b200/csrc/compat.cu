@@ -199,7 +199,7 @@ r0b200_sppark_error sppark_batch_NTT(uint32_t* d_inout, uint32_t lg_domain_size,
     if (lg_domain_size == 0) return;
     const size_t words = (size_t)poly_count << lg_domain_size;
     uint32_t* tmp = nullptr;
-    R0_CUDA(cudaMallocAsync(&tmp, words ? words * 4 : 16, c->stream));
+    R0_CUDA(r0_malloc_async(c, &tmp, words ? words * 4 : 16, c->stream));
     r0_eltwise_copy(c, tmp, d_inout, words);
     r0_ntt_expand_evaluate(c, d_inout, tmp, poly_count, (int)lg_domain_size, 0, 0);
     R0_CUDA(cudaFreeAsync(tmp, c->stream));
@@ -233,7 +233,7 @@ r0b200_sppark_error supra_poly_divide(uint32_t* polynomial, size_t poly_size, ui
   return swrap([&](r0b200_ctx* c) {
     R0_CHECK(remainder != nullptr && pow != nullptr, "poly_divide: null host pointer");
     uint32_t* rem_dev = nullptr;
-    R0_CUDA(cudaMallocAsync(&rem_dev, 16, c->stream));
+    R0_CUDA(r0_malloc_async(c, &rem_dev, 16, c->stream));
     r0_poly_divide(c, polynomial, poly_size, FpExt{{pow[0], pow[1], pow[2], pow[3]}}, rem_dev);
     R0_CUDA(cudaMemcpyAsync(remainder, rem_dev, 16, cudaMemcpyDeviceToHost, c->stream));
     R0_CUDA(cudaStreamSynchronize(c->stream));

@@ -38,10 +38,14 @@ r0b200_err r0b200_create(int device, r0b200_ctx** out) {
   R0_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   R0_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   // keep freed blocks in the stream-ordered pool instead of returning them to the OS between proofs
-  cudaMemPool_t pool;
-  R0_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  R0_CUDA(cudaMemPoolCreate(&c->pool, &props));
   uint64_t threshold = UINT64_MAX;
-  R0_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  R0_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
   r0_ntt_init_tables(c);
   r0_poseidon2_init(c);
   *out = c;
@@ -52,6 +56,7 @@ void r0b200_destroy(r0b200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->copy_stream);
   r0_ntt_free_tables(c);
   for (auto& r : c->phase_log) {
     cudaEventDestroy(r.a);
@@ -64,6 +69,7 @@ void r0b200_destroy(r0b200_ctx* c) {
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   delete c;
 }
 
@@ -147,7 +153,7 @@ r0b200_err r0b200_profile_end(r0b200_ctx* ctx, char* json_out, size_t cap) {
 r0b200_err r0b200_alloc(r0b200_ctx* ctx, size_t bytes, void** dptr) {
   CTX_BEGIN
   R0_CHECK(dptr != nullptr, "r0b200_alloc: null out pointer");
-  R0_CUDA(cudaMallocAsync(dptr, bytes ? bytes : 16, ctx->stream));
+  R0_CUDA(r0_malloc_async(ctx, dptr, bytes ? bytes : 16, ctx->stream));
   ctx->alloc_sizes[*dptr] = bytes;
   ctx->bytes_allocated += bytes;
   if (ctx->bytes_allocated > ctx->bytes_peak) ctx->bytes_peak = ctx->bytes_allocated;
@@ -326,7 +332,7 @@ r0b200_err r0b200_combos_divide(r0b200_ctx* ctx, uint32_t* combos, size_t nchunk
   size_t ndiv = pow_begin_host[nchunks];
   if (ndiv == 0) return nullptr;
   uint32_t* rem_dev = nullptr;
-  R0_CUDA(cudaMallocAsync(&rem_dev, ndiv * 16, ctx->stream));
+  R0_CUDA(r0_malloc_async(ctx, &rem_dev, ndiv * 16, ctx->stream));
   // round r divides every combo that still has an r-th point: the combos are independent polynomials, so one round
   // is three launches whatever the number of combos (6 rounds instead of 15 divisions for rv32im)
   for (uint32_t r = 0;; r++) {

@@ -460,7 +460,7 @@ struct Scratch {
   Ctx* c;
   void* d = nullptr;
   Scratch(Ctx* c_, const void* host, size_t bytes) : c(c_) {
-    R0_CUDA(cudaMallocAsync(&d, bytes ? bytes : 16, c->stream));
+    R0_CUDA(r0_malloc_async(c, &d, bytes ? bytes : 16, c->stream));
     if (bytes) {
       // The caller's buffer may be pinned (the header recommends pinned memory for witnesses), and a copy from pinned
       // memory is truly asynchronous: the caller could free or overwrite it before the GPU reads it. Stage through a
@@ -470,7 +470,7 @@ struct Scratch {
       R0_CUDA(cudaMemcpyAsync(d, stage.data(), bytes, cudaMemcpyHostToDevice, c->stream));
     }
   }
-  Scratch(Ctx* c_, size_t bytes) : c(c_) { R0_CUDA(cudaMallocAsync(&d, bytes ? bytes : 16, c->stream)); }
+  Scratch(Ctx* c_, size_t bytes) : c(c_) { R0_CUDA(r0_malloc_async(c, &d, bytes ? bytes : 16, c->stream)); }
   ~Scratch() { cudaFreeAsync(d, c->stream); }
   template <typename T>
   T* as() { return (T*)d; }

@@ -39,7 +39,7 @@ struct DevBuf {
   // `alloc_stream`: the stream the allocation is ordered on (default: the compute stream). The buffer is always
   // released on the compute stream, after the kernels that used it.
   DevBuf(Ctx* c_, size_t words_, cudaStream_t alloc_stream = nullptr) : c(c_), words(words_) {
-    R0_CUDA(cudaMallocAsync(&p, (words ? words : 4) * 4, alloc_stream ? alloc_stream : c->stream));
+    R0_CUDA(r0_malloc_async(c, &p, (words ? words : 4) * 4, alloc_stream ? alloc_stream : c->stream));
     c->bytes_allocated += words * 4;
     if (c->bytes_allocated > c->bytes_peak) c->bytes_peak = c->bytes_allocated;
   }
@@ -730,9 +730,9 @@ extern "C" r0b200_err r0b200_segment_upload(r0b200_ctx* ctx, uint32_t po2, const
   if (inj_index_len >= 2) {
     seg->index_len = inj_index_len;
     seg->nvals = inj_index_host[inj_index_len - 1];
-    R0_CUDA(cudaMallocAsync(&seg->d_index, inj_index_len * 4, cs));
-    R0_CUDA(cudaMallocAsync(&seg->d_offsets, std::max<size_t>(1, seg->nvals) * 4, cs));
-    R0_CUDA(cudaMallocAsync(&seg->d_values, std::max<size_t>(1, seg->nvals) * 4, cs));
+    R0_CUDA(r0_malloc_async(seg->ctx, &seg->d_index, inj_index_len * 4, cs));
+    R0_CUDA(r0_malloc_async(seg->ctx, &seg->d_offsets, std::max<size_t>(1, seg->nvals) * 4, cs));
+    R0_CUDA(r0_malloc_async(seg->ctx, &seg->d_values, std::max<size_t>(1, seg->nvals) * 4, cs));
     R0_CUDA(cudaMemcpyAsync(seg->d_index, inj_index_host, inj_index_len * 4, cudaMemcpyHostToDevice, cs));
     R0_CUDA(cudaMemcpyAsync(seg->d_offsets, inj_offsets_host, seg->nvals * 4, cudaMemcpyHostToDevice, cs));
     R0_CUDA(cudaMemcpyAsync(seg->d_values, inj_values_host, seg->nvals * 4, cudaMemcpyHostToDevice, cs));
@@ -863,7 +863,7 @@ extern "C" r0b200_err r0b200_witness_upload(r0b200_ctx* ctx, int circuit, uint32
     if (!src[g]) continue;   // accum is normally not known yet (it depends on the mix drawn by prove_begin)
     const size_t count = desc.group_sizes[g];
     w->words[g] = count * cycles;
-    R0_CUDA(cudaMallocAsync(&w->coeffs[g], w->words[g] * 4, ctx->copy_stream));
+    R0_CUDA(r0_malloc_async(ctx, &w->coeffs[g], w->words[g] * 4, ctx->copy_stream));
     for (size_t c0 = 0; c0 < count; c0 += chunk) {
       const size_t nc = std::min(chunk, count - c0);
       R0_CUDA(cudaMemcpyAsync(w->coeffs[g] + c0 * cycles, src[g] + c0 * cycles, nc * cycles * 4, cudaMemcpyHostToDevice,

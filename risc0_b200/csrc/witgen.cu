@@ -261,15 +261,15 @@ r0b200_trace* r0_trace_upload(Ctx* c, const r0b200_preflight_trace* h, uint32_t 
   t->bigint_len = h->bigint_bytes_len;
   t->split = h->table_split_cycle;
   cudaStream_t s = stream ? stream : c->stream;
-  R0_CUDA(cudaMallocAsync(&t->d_cycles, (size_t)cycles * sizeof(PreflightCycle), s));
-  R0_CUDA(cudaMallocAsync(&t->d_txns, std::max<size_t>(1, h->txns_len) * sizeof(MemoryTxn), s));
-  R0_CUDA(cudaMallocAsync(&t->d_bigint, std::max<size_t>(16, h->bigint_bytes_len), s));
-  R0_CUDA(cudaMallocAsync(&t->d_order, (size_t)cycles * 4, s));
-  R0_CUDA(cudaMallocAsync(&t->d_order_all, (size_t)cycles * 4, s));
-  R0_CUDA(cudaMallocAsync(&t->d_tables, (256 + 65536 + NKEYS) * 4, s));
-  R0_CUDA(cudaMallocAsync(&t->d_err, 16, s));
-  R0_CUDA(cudaMallocAsync(&t->d_shared, sizeof(WShared), s));
-  R0_CUDA(cudaMallocAsync(&t->d_layout, sizeof(kLayoutHost), s));
+  R0_CUDA(r0_malloc_async(c, &t->d_cycles, (size_t)cycles * sizeof(PreflightCycle), s));
+  R0_CUDA(r0_malloc_async(c, &t->d_txns, std::max<size_t>(1, h->txns_len) * sizeof(MemoryTxn), s));
+  R0_CUDA(r0_malloc_async(c, &t->d_bigint, std::max<size_t>(16, h->bigint_bytes_len), s));
+  R0_CUDA(r0_malloc_async(c, &t->d_order, (size_t)cycles * 4, s));
+  R0_CUDA(r0_malloc_async(c, &t->d_order_all, (size_t)cycles * 4, s));
+  R0_CUDA(r0_malloc_async(c, &t->d_tables, (256 + 65536 + NKEYS) * 4, s));
+  R0_CUDA(r0_malloc_async(c, &t->d_err, 16, s));
+  R0_CUDA(r0_malloc_async(c, &t->d_shared, sizeof(WShared), s));
+  R0_CUDA(r0_malloc_async(c, &t->d_layout, sizeof(kLayoutHost), s));
   R0_CUDA(cudaMemcpyAsync(t->d_cycles, h->cycles, (size_t)cycles * sizeof(PreflightCycle), cudaMemcpyHostToDevice, s));
   if (h->txns_len)
     R0_CUDA(cudaMemcpyAsync(t->d_txns, h->txns, (size_t)h->txns_len * sizeof(MemoryTxn), cudaMemcpyHostToDevice, s));
@@ -315,7 +315,7 @@ void r0_accum_rv32im(Ctx* c, r0b200_trace* t, uint32_t* data, uint32_t* accum, u
   launch_step_accum(c->stream, t->d_shared, t->d_order_all, n);
   const uint32_t nblocks = (n + SCAN_SEG - 1) / SCAN_SEG;
   uint32_t* tot = nullptr;
-  R0_CUDA(cudaMallocAsync(&tot, (size_t)4 * nblocks * 4, c->stream));
+  R0_CUDA(r0_malloc_async(c, &tot, (size_t)4 * nblocks * 4, c->stream));
   uint32_t* last4 = accum + (size_t)(cols - 4) * rows;
   k_scan_cols<false><<<dim3(nblocks, 4), SCAN_T, 0, c->stream>>>(last4, rows, n, tot, nblocks);
   k_scan_totals<<<4, SCAN_T, 0, c->stream>>>(tot, nblocks);
