@@ -993,10 +993,15 @@ void r0_ntt_expand_evaluate(Ctx* c, uint32_t* out, const uint32_t* in, size_t co
   R0_CUDA(cudaGetLastError());
 }
 
+namespace r0 {
+bool r0_bit_reverse_tma(Ctx* c, uint32_t* io, size_t count, int k);
+}
+
 void r0_bit_reverse(Ctx* c, uint32_t* io, size_t count, int k) {
   PhaseScope ph(c, "bit_reverse", 8.0 * (double)count * (double)(size_t(1) << k));
   R0_CHECK(k >= 0 && k <= 30, "batch_bit_reverse: size out of range");
   if (count == 0 || k < 2) return;
+  if (r0_bit_reverse_tma(c, io, count, k)) return;   // k >= 10: TMA tensor loads / stores (bitrev_tma.cu)
   int t = k / 2 < 5 ? k / 2 : 5;
   for (size_t c0 = 0; c0 < count; c0 += 65535) {
     size_t nc = count - c0 < 65535 ? count - c0 : 65535;

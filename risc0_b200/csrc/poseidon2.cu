@@ -70,12 +70,16 @@ __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
 //   bit 0: M_ext first stage (t0..t3 incl. doublings)   bit 1: M_ext second stage (t4..t7)
 //   bit 2: M_ext column sums                            bit 3: M_ext final "+ column sum"
 //   bit 4: partial-round sum tree                       bit 5: partial-round "+ sum"
+//   bit 7: EVERY addition (and the Montgomery subtraction) pinned to the alu pipe as a three-input IADD3
+//   bit 8: bits 0-5 choose between the two PINNED forms (set = three-input IADD3, clear = IMAD x*1+y); without it a
+//          set bit only writes a plain add, which ptxas re-issues as IMAD.IADD / IADD3 to balance instruction counts
 //   bit 6: round constants enter the S-box unreduced: x = c + rc - P in (-P, P) is a legal signed operand of the x^7
 //          chain, so the modular add (IADD3 + VIADDMNMX) becomes one IADD3
 // The best mask is measured (tools/bench_hash.py --mode, profiles/r2_poseidon2_modes.log); R0B200_P2_MODE overrides it.
 template <int MODE, int BIT>
 __device__ __forceinline__ uint32_t add_m(uint32_t a, uint32_t b) {
   if (MODE & 128) return fp_add_alu(a, b);
+  if (MODE & 256) return (MODE & (1 << BIT)) ? fp_add_alu(a, b) : fp_add_fma(a, b);   // both choices pinned
   if (MODE & (1 << BIT)) return fp_add(a, b);
   return fp_add_fma(a, b);
 }
@@ -83,15 +87,15 @@ template <int MODE>
 __device__ __forceinline__ uint32_t sbox7_rc(uint32_t x, uint32_t rc) {
   if (MODE & 64) {
     int32_t x1 = (int32_t)(x + rc - P);   // in (-P, P)
-    if (MODE & 128) asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(x1) : "r"(x), "r"(rc), "r"(c_zero - P));
-    constexpr bool A = (MODE & 128) != 0;
+    if (MODE & 384) asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(x1) : "r"(x), "r"(rc), "r"(c_zero - P));
+    constexpr bool A = (MODE & 384) != 0;
     const int32_t x2 = mul_signed<A>(x1, x1);
     const int32_t x4 = mul_signed<A>(x2, x2);
     const int32_t x6 = mul_signed<A>(x4, x2);
     const uint32_t r = (uint32_t)mul_signed<A>(x6, x1);
     return umin32(r, r + P);
   }
-  if (MODE & 128) return sbox7<true>(fp_add_alu(x, rc));
+  if (MODE & 384) return sbox7<true>(fp_add_alu(x, rc));
   return sbox7(fp_add(x, rc));
 }
 
@@ -154,7 +158,7 @@ __device__ __forceinline__ void partial_round(uint32_t (&c)[24], int r) {
     const uint32_t q = __umulhi(c[i], c_diag_q[i]);
     uint32_t r = c[i] * c_diag_n[i] - q * P;
     r = umin32(r, r - P);
-    c[i] = (MODE & 128) ? fp_add_alu(r, sum) : (MODE & 32) ? fp_add(r, sum) : fp_add_fma(r, sum);
+    c[i] = add_m<MODE, 5>(r, sum);
   }
 }
 
@@ -302,12 +306,12 @@ static int p2_mode() {
   static const int mode = getenv("R0B200_P2_MODE") ? atoi(getenv("R0B200_P2_MODE")) : R0_P2_DEFAULT_MODE;
   return mode;
 }
-// the fold kernels are compiled for the default schedule and the two reference points of the mode experiment
+// the fold kernels are compiled for the default schedule and the two all-alu reference points of the mode experiment
 #define P2_FOLD_DISPATCH(CALL)                         \
   switch (p2_mode()) {                                 \
-    case 32: { constexpr int M = 32; CALL; } break;    \
     case 128: { constexpr int M = 128; CALL; } break;  \
-    default: { constexpr int M = 192; CALL; } break;   \
+    case 192: { constexpr int M = 192; CALL; } break;  \
+    default: { constexpr int M = R0_P2_DEFAULT_MODE; CALL; } break; \
   }
 
 void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
@@ -318,6 +322,7 @@ void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows,
 #define P2_ROWS(M) case M: p2_hash_rows_kernel<M><<<grid, 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
   switch (p2_mode()) {
     P2_ROWS(0) P2_ROWS(32) P2_ROWS(63) P2_ROWS(64) P2_ROWS(96) P2_ROWS(120) P2_ROWS(127) P2_ROWS(128) P2_ROWS(192)
+    P2_ROWS(288) P2_ROWS(290) P2_ROWS(300) P2_ROWS(304) P2_ROWS(364) P2_ROWS(372)
     default: throw std::invalid_argument("R0B200_P2_MODE: mask not compiled in");
   }
 #undef P2_ROWS
