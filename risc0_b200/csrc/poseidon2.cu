@@ -203,6 +203,82 @@ __global__ void __launch_bounds__(256) p2_hash_rows_kernel(uint32_t* __restrict_
   o[1] = make_uint4(c[4], c[5], c[6], c[7]);
 }
 
+
+// ---- experiment variants of hash_rows (R0B200_P2_VARIANT, tools/bench_hash.py): occupancy against per-thread ILP ----
+// V = 1: the same kernel under a 32-register cap (8 blocks of 256 = all 64 warp slots)
+// V = 2: two rows per thread, the two states carried through every round together (twice the independent work per
+//        warp at half the warps)
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB) p2_hash_rows_occ_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix,
+                                                                   size_t rows, uint32_t cols) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  uint32_t c[24];
+#pragma unroll
+  for (int i = 0; i < 24; i++) c[i] = 0;
+  uint32_t done = 0;
+  do {
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = (done + i < cols) ? matrix[(size_t)(done + i) * rows + row] : 0u;
+    p2_permute_m<MODE>(c);
+    done += 16;
+  } while (done < cols);
+  uint4* o = reinterpret_cast<uint4*>(out + row * 8);
+  o[0] = make_uint4(c[0], c[1], c[2], c[3]);
+  o[1] = make_uint4(c[4], c[5], c[6], c[7]);
+}
+
+template <int MODE>
+__device__ __forceinline__ void p2_permute2_m(uint32_t (&a)[24], uint32_t (&b)[24]) {
+  m_ext<MODE>(a);
+  m_ext<MODE>(b);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+    full_round<MODE>(a, r);
+    full_round<MODE>(b, r);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 21; r++) {
+    partial_round<MODE>(a, r);
+    partial_round<MODE>(b, r);
+  }
+#pragma unroll 1
+  for (int r = 4; r < 8; r++) {
+    full_round<MODE>(a, r);
+    full_round<MODE>(b, r);
+  }
+}
+
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) p2_hash_rows2_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix,
+                                                                size_t rows, uint32_t cols) {
+  // rows is even for every caller that reaches this kernel (host checks); thread t takes rows t and t + rows / 2
+  const size_t half = rows >> 1;
+  const size_t r0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r0 >= half) return;
+  const size_t r1 = r0 + half;
+  uint32_t a[24], b[24];
+#pragma unroll
+  for (int i = 0; i < 24; i++) a[i] = b[i] = 0;
+  uint32_t done = 0;
+  do {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const bool in = done + i < cols;
+      a[i] = in ? matrix[(size_t)(done + i) * rows + r0] : 0u;
+      b[i] = in ? matrix[(size_t)(done + i) * rows + r1] : 0u;
+    }
+    p2_permute2_m<MODE>(a, b);
+    done += 16;
+  } while (done < cols);
+  uint4* o = reinterpret_cast<uint4*>(out + r0 * 8);
+  o[0] = make_uint4(a[0], a[1], a[2], a[3]);
+  o[1] = make_uint4(a[4], a[5], a[6], a[7]);
+  o = reinterpret_cast<uint4*>(out + r1 * 8);
+  o[0] = make_uint4(b[0], b[1], b[2], b[3]);
+  o[1] = make_uint4(b[4], b[5], b[6], b[7]);
+}
+
 __device__ __forceinline__ void load_pair(uint32_t (&c)[24], const uint32_t* __restrict__ in) {
   const uint4* p = reinterpret_cast<const uint4*>(in);
   uint4 a = p[0], b = p[1], d = p[2], e = p[3];
@@ -319,6 +395,22 @@ void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows,
   if (rows == 0) return;
   R0_CHECK(cols <= 0xffffffffull, "hash_rows: too many columns");
   const unsigned grid = (unsigned)((rows + 255) / 256);
+  static const int variant = getenv("R0B200_P2_VARIANT") ? atoi(getenv("R0B200_P2_VARIANT")) : 0;
+  if (variant && (rows & 1) == 0) {
+    constexpr int M = R0_P2_DEFAULT_MODE;
+    const unsigned g2 = (unsigned)((rows / 2 + 127) / 128);
+    switch (variant) {
+      case 1: p2_hash_rows_occ_kernel<M, 8><<<grid, 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
+      case 2: p2_hash_rows2_kernel<M, 1><<<g2, 128, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
+      case 3: p2_hash_rows2_kernel<M, 6><<<g2, 128, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
+      case 4: p2_hash_rows2_kernel<M, 8><<<g2, 128, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
+      case 5: p2_hash_rows_occ_kernel<M, 7><<<grid, 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
+      default: throw std::invalid_argument("R0B200_P2_VARIANT: unknown variant");
+    }
+    count_launch(c);
+    R0_CUDA(cudaGetLastError());
+    return;
+  }
 #define P2_ROWS(M) case M: p2_hash_rows_kernel<M><<<grid, 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
   switch (p2_mode()) {
     P2_ROWS(0) P2_ROWS(32) P2_ROWS(63) P2_ROWS(64) P2_ROWS(96) P2_ROWS(120) P2_ROWS(127) P2_ROWS(128) P2_ROWS(192)
