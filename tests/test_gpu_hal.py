@@ -91,6 +91,20 @@ def test_batch_bit_reverse(hal, lg, count):
     assert np.array_equal(io.view(), vals)
 
 
+@pytest.mark.parametrize("lg,count,first", [(10, 3, 1), (12, 5, 2), (16, 7, 3)])
+def test_batch_bit_reverse_on_a_slice(hal, lg, count, first):
+    # the TMA kernel (csrc/bitrev_tma.cu) describes the columns it is given as one tensor: a slice that starts at a
+    # later column must leave the columns before and after it untouched
+    rng = rng_for("brev_slice", lg, count)
+    total = count + first + 1
+    vals = O.rand_elems(rng, total << lg)
+    io = hal.copy_from_elem("io", vals)
+    hal.batch_bit_reverse(io.slice(first << lg, count << lg), count)
+    want = vals.copy()
+    want[first << lg:(first + count) << lg] = O.batch_bit_reverse(vals[first << lg:(first + count) << lg], count)
+    assert np.array_equal(io.view(), want)
+
+
 def test_batch_evaluate_any(hal):
     # hal testutil: 223 polys x 2^16, 865 evaluation points
     rng = rng_for("evalany")

@@ -127,6 +127,41 @@ def test_segment_upload_pipeline(hal):
     assert np.array_equal(got0, want[0]) and np.array_equal(got1, want[1]) and np.array_equal(again, want[0])
 
 
+def test_two_contexts_prove_concurrently_on_one_gpu():
+    # bench.py keeps two segments in flight per GPU: two contexts (own stream, copy stream and memory pool), one host
+    # thread each, proving at the same time. Every seal must equal the one a single context produces.
+    import threading
+    pfs = [PF.PreflightResults(seg(n), (61, 62, 63, 64)) for n in ("loop_po2_13", "all_insn")]
+    solo = B200Hal(0, "poseidon2")
+    want = [SegmentProver(solo).prove_core(pf)[0] for pf in pfs]
+    solo.close()
+    hals = [B200Hal(0, "poseidon2") for _ in range(2)]
+    got, errs = [[], []], []
+
+    def worker(w):
+        try:
+            p = SegmentProver(hals[w])
+            for r in range(4):
+                pf = pfs[(w + r) % 2]
+                up = p.upload_segment(pf)
+                got[w].append(((w + r) % 2, p.prove_segment(up)[0]))
+        except BaseException as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(w,)) for w in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for h in hals:
+        h.close()
+    assert not errs, errs
+    for w in range(2):
+        assert len(got[w]) == 4
+        for which, seal in got[w]:
+            assert np.array_equal(seal, want[which])
+
+
 def test_reference_witgen_symbols(hal):
     # risc0_circuit_rv32im_cuda_witgen / _cuda_accum with the reference's structs (rv32im-sys/src/lib.rs:21-119),
     # device buffers + host trace, as rv32im/src/prove/hal/cuda.rs:60-157 calls them
