@@ -30,7 +30,7 @@ void r0_fri_fold(r0::Ctx* c, uint32_t* out, const uint32_t* in, size_t count, co
 void r0_mix_poly_coeffs(r0::Ctx* c, uint32_t* out, const r0::FpExt& mix_start, const r0::FpExt& mix, const uint32_t* in,
                         const uint32_t* combos_host, size_t input_size, size_t count);
 void r0_batch_evaluate_any(r0::Ctx* c, const uint32_t* coeffs, size_t n, const uint32_t* which_dev,
-                           const uint32_t* xs_dev, uint32_t* out_dev, size_t eval_count, size_t distinct_polys = 0);
+                           const uint32_t* xs_dev, uint32_t* out_dev, size_t eval_count, size_t distinct_polys = 0, const uint32_t* which_host = nullptr);
 void r0_gather_sample(r0::Ctx* c, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride);
 void r0_scatter(r0::Ctx* c, uint32_t* into, const uint32_t* index_host, size_t index_len, const uint32_t* offsets_host,
                 const uint32_t* values_host);

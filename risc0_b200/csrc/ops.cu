@@ -167,34 +167,71 @@ __global__ void k_eval_tables(FpExt* xt /*[E][256]*/, FpExt* xq /*[E][EV_CH]*/, 
   for (int c = t; c < nchunks; c += blockDim.x) xc[(size_t)e * nchunks + c] = ext_pow(xblk, c);
 }
 
+// R consecutive evaluations e0 .. e0 + R - 1 of the SAME polynomial (the taps of one register at its back-points are
+// adjacent in the tap set): the coefficients are read once and multiplied into R x 4 lazy 64-bit accumulators. Two
+// products (< 2 P^2) on top of a folded accumulator (< P 2^32) stay under 2^64, so the high word is folded every second
+// coefficient only.
+// (lo, hi) += a * b as ONE IMAD.WIDE with a 64-bit accumulator operand: the carry-chained pair is the form ptxas folds
+// that way. Written in C the zero-extended operand of a predicated load became a 64 x 32-bit product (IMAD.WIDE + IMAD
+// + IADD per term), and a chain of mad.wide.u32 is re-associated into IMAD.WIDE + IADD3 / IADD3.X trees (5 alu-pipe
+// cycles per term instead of 2).
+__device__ __forceinline__ void mad_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+
+template <int R, bool FULL>
 __global__ void __launch_bounds__(EV_T) k_eval_partial(FpExt* partial, const uint32_t* coeffs, size_t n,
-                                                       const uint32_t* which, const FpExt* xt, const FpExt* xq,
-                                                       const FpExt* xc, int nchunks) {
-  __shared__ FpExt q[EV_CH];
+                                                       const uint32_t* which, const uint32_t* run_start,
+                                                       const FpExt* xt, const FpExt* xq, const FpExt* xc, int nchunks) {
+  __shared__ FpExt q[R][EV_CH];
   __shared__ FpExt red[EV_T];
-  const int e = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
-  if (t < EV_CH) q[t] = xq[(size_t)e * EV_CH + t];
+  const int chunk = blockIdx.x, t = threadIdx.x;
+  const uint32_t e0 = run_start[blockIdx.y];
+  for (int w = t; w < R * EV_CH; w += EV_T) q[w / EV_CH][w % EV_CH] = xq[(size_t)(e0 + w / EV_CH) * EV_CH + (w % EV_CH)];
   __syncthreads();
-  const uint32_t* poly = coeffs + (size_t)which[e] * n;
   const size_t base = (size_t)chunk * EV_T * EV_CH;
-  uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 8
-  for (int j = 0; j < EV_CH; j++) {
-    const size_t i = base + (size_t)j * EV_T + t;
-    const uint32_t c = i < n ? poly[i] : 0u;
-    lazy_mac(a0, c, q[j].c[0]);
-    lazy_mac(a1, c, q[j].c[1]);
-    lazy_mac(a2, c, q[j].c[2]);
-    lazy_mac(a3, c, q[j].c[3]);
+  const uint32_t* poly = coeffs + (size_t)which[e0] * n + base + t;   // FULL: every index of the chunk is < n
+  const uint32_t left = FULL ? 0u : (uint32_t)(n > base + t ? (n - base - t + EV_T - 1) / EV_T : 0);   // valid j of this thread
+  uint32_t lo[R][4], hi[R][4];
+#pragma unroll
+  for (int r = 0; r < R; r++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) lo[r][k] = hi[r][k] = 0;
+#pragma unroll 4
+  for (int j = 0; j < EV_CH; j += 2) {
+    uint32_t c0, c1;
+    if (FULL) {
+      c0 = poly[(size_t)j * EV_T];
+      c1 = poly[(size_t)(j + 1) * EV_T];
+    } else {
+      c0 = (uint32_t)j < left ? poly[(size_t)j * EV_T] : 0u;
+      c1 = (uint32_t)(j + 1) < left ? poly[(size_t)(j + 1) * EV_T] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        mad_wide(lo[r][k], hi[r][k], c0, q[r][j].c[k]);
+        mad_wide(lo[r][k], hi[r][k], c1, q[r][j + 1].c[k]);
+        hi[r][k] = umin32(hi[r][k], hi[r][k] - P);
+      }
+    }
   }
-  FpExt s{{lazy_finish(a0), lazy_finish(a1), lazy_finish(a2), lazy_finish(a3)}};
-  red[t] = ext_mul(s, xt[(size_t)e * EV_T + t]);
-  __syncthreads();
-  for (int w = EV_T / 2; w > 0; w >>= 1) {
-    if (t < w) red[t] = ext_add(red[t], red[t + w]);
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t e = e0 + r;
+    FpExt s;
+#pragma unroll
+    for (int k = 0; k < 4; k++) s.c[k] = lazy_finish(((uint64_t)hi[r][k] << 32) | lo[r][k]);
+    if (r) __syncthreads();   // red is reused
+    red[t] = ext_mul(s, xt[(size_t)e * EV_T + t]);
     __syncthreads();
+    for (int w = EV_T / 2; w > 0; w >>= 1) {
+      if (t < w) red[t] = ext_add(red[t], red[t + w]);
+      __syncthreads();
+    }
+    if (t == 0) partial[(size_t)e * nchunks + chunk] = ext_mul(red[0], xc[(size_t)e * nchunks + chunk]);
   }
-  if (t == 0) partial[(size_t)e * nchunks + chunk] = ext_mul(red[0], xc[(size_t)e * nchunks + chunk]);
 }
 
 __global__ void k_eval_final(FpExt* out, const FpExt* partial, int nchunks) {
@@ -529,7 +566,7 @@ void r0_mix_poly_coeffs(Ctx* c, uint32_t* out, const FpExt& mix_start, const FpE
 // distinct_polys: how many different polynomials the evaluations touch (SURVEY 8d counts 4 * P_distinct * n algorithmic
 // bytes: evaluations of one register at several back-points re-read its polynomial through L2, not HBM); 0 = unknown
 void r0_batch_evaluate_any(Ctx* c, const uint32_t* coeffs, size_t n, const uint32_t* which_dev, const uint32_t* xs_dev,
-                           uint32_t* out_dev, size_t eval_count, size_t distinct_polys) {
+                           uint32_t* out_dev, size_t eval_count, size_t distinct_polys, const uint32_t* which_host_in) {
   const size_t distinct = distinct_polys && distinct_polys < eval_count ? distinct_polys : eval_count;
   PhaseScope ph(c, "batch_evaluate_any", 4.0 * (double)n * (double)distinct);
   if (eval_count == 0) return;
@@ -539,15 +576,57 @@ void r0_batch_evaluate_any(Ctx* c, const uint32_t* coeffs, size_t n, const uint3
   Scratch xq(c, eval_count * EV_CH * sizeof(FpExt));
   Scratch xc(c, eval_count * nchunks * sizeof(FpExt));
   Scratch partial(c, eval_count * nchunks * sizeof(FpExt));
+  // runs of consecutive evaluations of one polynomial, cut to at most 4, grouped by length: one launch per length
+  // (callers that built `which` on the host pass it along; the C-ABI form only has the device copy)
+  std::vector<uint32_t> which_copy;
+  const uint32_t* which_host = which_host_in;
+  if (!which_host) {
+    which_copy.resize(eval_count);
+    R0_CUDA(cudaMemcpyAsync(which_copy.data(), which_dev, eval_count * 4, cudaMemcpyDeviceToHost, c->stream));
+    R0_CUDA(cudaStreamSynchronize(c->stream));
+    which_host = which_copy.data();
+  }
+  const bool full = n % per_block == 0;
+  std::vector<uint32_t> runs[4];
+  for (size_t e = 0; e < eval_count;) {
+    size_t len = 1;
+    while (len < 4 && e + len < eval_count && which_host[e + len] == which_host[e]) len++;
+    runs[len - 1].push_back((uint32_t)e);
+    e += len;
+  }
   for (size_t e0 = 0; e0 < eval_count; e0 += 65535) {
     size_t ne = eval_count - e0 < 65535 ? eval_count - e0 : 65535;
     k_eval_tables<<<(unsigned)ne, EV_T, 0, c->stream>>>(xt.as<FpExt>() + e0 * EV_T, xq.as<FpExt>() + e0 * EV_CH,
                                                         xc.as<FpExt>() + e0 * nchunks, (const FpExt*)xs_dev + e0, nchunks);
-    k_eval_partial<<<dim3(nchunks, (unsigned)ne), EV_T, 0, c->stream>>>(
-        partial.as<FpExt>() + e0 * nchunks, coeffs, n, which_dev + e0, xt.as<FpExt>() + e0 * EV_T,
-        xq.as<FpExt>() + e0 * EV_CH, xc.as<FpExt>() + e0 * nchunks, nchunks);
+    count_launch(c);
+  }
+  for (int len = 1; len <= 4; len++) {
+    const std::vector<uint32_t>& rs = runs[len - 1];
+    for (size_t r0 = 0; r0 < rs.size(); r0 += 65535) {
+      const size_t nr = rs.size() - r0 < 65535 ? rs.size() - r0 : 65535;
+      Scratch d_runs(c, rs.data() + r0, nr * 4);
+      const dim3 grid(nchunks, (unsigned)nr);
+#define EV_LAUNCH(R)                                                                                                     \
+  if (full)                                                                                                              \
+    k_eval_partial<R, true><<<grid, EV_T, 0, c->stream>>>(partial.as<FpExt>(), coeffs, n, which_dev, d_runs.as<uint32_t>(), \
+                                                          xt.as<FpExt>(), xq.as<FpExt>(), xc.as<FpExt>(), nchunks);     \
+  else                                                                                                                   \
+    k_eval_partial<R, false><<<grid, EV_T, 0, c->stream>>>(partial.as<FpExt>(), coeffs, n, which_dev, d_runs.as<uint32_t>(), \
+                                                           xt.as<FpExt>(), xq.as<FpExt>(), xc.as<FpExt>(), nchunks)
+      switch (len) {
+        case 1: EV_LAUNCH(1); break;
+        case 2: EV_LAUNCH(2); break;
+        case 3: EV_LAUNCH(3); break;
+        default: EV_LAUNCH(4); break;
+      }
+#undef EV_LAUNCH
+      count_launch(c);
+    }
+  }
+  for (size_t e0 = 0; e0 < eval_count; e0 += 65535) {
+    size_t ne = eval_count - e0 < 65535 ? eval_count - e0 : 65535;
     k_eval_final<<<(unsigned)ne, 256, 0, c->stream>>>((FpExt*)out_dev + e0, partial.as<FpExt>() + e0 * nchunks, nchunks);
-    count_launch(c, 3);
+    count_launch(c);
   }
   R0_CUDA(cudaGetLastError());
 }

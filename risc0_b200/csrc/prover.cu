@@ -382,7 +382,7 @@ class SegmentProver {
         const size_t b = g < groups_.size() ? taps_.group_begin[g] : ntaps;
         const size_t e = g < groups_.size() ? taps_.group_begin[g + 1] : ntaps + CHECK_SIZE;
         const PolyGroup& pg = g < groups_.size() ? groups_[g] : check;
-        r0_batch_evaluate_any(c_, pg.coeffs.p, cycles_, d_which.p + b, d_xs.p + 4 * b, d_out.p + 4 * b, e - b, pg.count);
+        r0_batch_evaluate_any(c_, pg.coeffs.p, cycles_, d_which.p + b, d_xs.p + 4 * b, d_out.p + 4 * b, e - b, pg.count, which.data() + b);
       }
       R0_CUDA(cudaMemcpyAsync(eval_u.data(), d_out.p, eval_u.size() * 16, cudaMemcpyDeviceToHost, c_->stream));
       R0_CUDA(cudaStreamSynchronize(c_->stream));
