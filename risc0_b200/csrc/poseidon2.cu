@@ -21,6 +21,12 @@ __constant__ uint32_t c_rc_partial[21];
 __constant__ uint32_t c_diag[24];
 __constant__ uint32_t c_diag_n[24];   // M_INT_DIAG_HZN in NORMAL form: x~ * d mod P keeps x~'s Montgomery form
 __constant__ uint32_t c_diag_q[24];   // floor(d * 2^32 / P): Shoup's precomputed quotient for multiplying by the constant d
+// ---- tensor-core partial rounds (hash_rows variant 6, see p2_hash_rows_tc_kernel) -------------------------------------
+__constant__ uint32_t c_Dm[20];      // D_k = sum_{i>=1} d_i^k, Montgomery form
+__constant__ uint32_t c_d21_n[24];   // d_i^21 in normal form, and its Shoup quotient
+__constant__ uint32_t c_d21_q[24];
+// B operands of the two constant matrices as mma.m16n8k32 fragments: [matrix][(ob * 7 + pos) * 3 + kt][lane] -> (b0, b1)
+__device__ uint2 g_p2_bfrag[2][63 * 32];
 __constant__ uint32_t c_one;  // = 1, opaque to the compiler: a * c_one + b is an IMAD, i.e. an add on the fma pipe
 __constant__ uint32_t c_zero;  // = 0, opaque to the compiler: a + b + c_zero is a genuine three-input IADD3 (alu pipe)
 
@@ -279,6 +285,176 @@ __global__ void __launch_bounds__(128, MINB) p2_hash_rows2_kernel(uint32_t* __re
   o[1] = make_uint4(b[4], b[5], b[6], b[7]);
 }
 
+// ---- hash_rows with the 21 partial rounds' linear algebra on the INT8 tensor cores (R0B200_P2_VARIANT=6) -------------
+// The partial rounds only touch element 0 non-linearly. Writing v_i (i >= 1) for the state at their start and s_r for
+// the sum a round adds to every element:  x_i after the 21 rounds = d_i^21 v_i + sum_j d_i^(20-j) s_j, and
+// s_r = z_r + sum_i d_i^r v_i + sum_{j<r} D_(r-1-j) s_j with z_r the S-box output of round r and D_k = sum_i d_i^k.
+// So the 21 x 24 diagonal multiplications become two constant matrix-vector products per permutation,
+//     A = M1 v  (21 x 23, before the rounds)     and     B = M2 s  (23 x 21, after them),
+// plus a 21-step scalar recurrence. The products run as u8 x u8 -> s32 mma.sync (IMMA.16832) over a whole warp's 32
+// permutations: a field word IS four u8 limbs in the K direction of the A fragment (k = 4 i + limb), the B operand holds
+// the limbs of (constant * 2^32 mod P) shifted to the seven product positions, each accumulator stays below 2^23, and
+// the seven position sums are folded back to one Montgomery word per output exactly
+// (sum_p T_p 2^(8p) = H 2^32 + L  ->  H mod P + L 2^-32 mod P). Everything is integer and exact: same digests
+// (the whole Poseidon2 test set passes with R0B200_P2_VARIANT=6).
+// Measured (2^22 x 64, profiles/r2_poseidon2_tensor.log): 1.92 Gperm/s against 2.15 for the register kernel, so it stays
+// opt-in. It removes 5.2 k of the 29.9 k integer pipe-cycles of a permutation, but as built its phases do not overlap
+// well enough: removing in turn the 252 IMMAs (+ their B-fragment loads, 64 KB of L1 traffic per warp and
+// permutation), the 21-step recurrence and the 48 recombinations brings 8.75 ms down to 6.46 / 6.94 / 7.38 ms, all
+// three to 5.05 ms (the full rounds). IMMA.16832 issues once per 8.4 cycles per sub-partition (1958 MAC/clk/SM,
+// tools/ubench/mma_u8.cu). Next steps if picked up again: B fragments shared by both row tiles, limb-major K (16
+// instead of 21 MMAs per output block), 64 registers for 32 warps per SM.
+__device__ __forceinline__ void imma_u8(int (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+// seven position sums (each < 2^23) of one output -> the Montgomery word of sum_i c_i v_i
+__device__ __forceinline__ uint32_t tc_recombine(int t0, int t1, int t2, int t3, int t4, int t5, int t6) {
+  const uint32_t u0 = (uint32_t)t1 * 256u + (uint32_t)t0;
+  const uint32_t u1 = (uint32_t)t3 * 256u + (uint32_t)t2;
+  const uint32_t u2 = (uint32_t)t5 * 256u + (uint32_t)t4;
+  const uint64_t l64 = (uint64_t)u1 * 65536u + u0;
+  const uint64_t h = (uint64_t)(uint32_t)t6 * 65536u + u2 + (l64 >> 32);     // < 2^40
+  const uint32_t l = (uint32_t)l64;
+  // L * 2^-32 mod P: m = L P^-1, (L - m P) / 2^32 = -hi(m P)
+  const uint32_t m = l * MONT_PINV;
+  const uint32_t nh = 0u - __umulhi(m, P);
+  const uint32_t r0 = umin32(nh, nh + P);
+  // H mod P with H = hh 2^32 + hl. Field words and the constants are < P < 0x78000001, so their top limbs are <= 0x78:
+  // t6 <= 23 * 0x78^2 < 2^18.4, H < 2^34.5, hh <= 5 and hh * (2^32 mod P) < 5 * 2^28 < 2 P fits 32 bits.
+  uint32_t r1 = (uint32_t)(h >> 32) * MONT_ONE;
+  r1 = umin32(r1, r1 - P);
+  uint32_t r2 = (uint32_t)h;
+  r2 = umin32(r2, r2 - P);
+  r2 = umin32(r2, r2 - P);
+  return fp_add(fp_add(r0, r1), r2);
+}
+
+template <int MODE>
+__device__ __forceinline__ void tc_matvec(uint32_t* dst /* warp's [32][28] words out */, const uint32_t* src /* same, in */,
+                                         const uint2* __restrict__ bfrag, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll 1
+  for (int mt = 0; mt < 2; mt++) {
+    uint32_t a[3][4];
+#pragma unroll
+    for (int kt = 0; kt < 3; kt++) {
+      const uint32_t* r0 = src + (mt * 16 + g) * 28 + kt * 8 + tig;
+      a[kt][0] = r0[0];
+      a[kt][1] = r0[8 * 28];
+      a[kt][2] = r0[4];
+      a[kt][3] = r0[8 * 28 + 4];
+    }
+#pragma unroll 1
+    for (int ob = 0; ob < 3; ob++) {
+      int acc[7][4];
+#pragma unroll
+      for (int p = 0; p < 7; p++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[p][q] = 0;
+#pragma unroll
+        for (int kt = 0; kt < 3; kt++) imma_u8(acc[p], a[kt], __ldg(&bfrag[((ob * 7 + p) * 3 + kt) * 32 + lane]));
+      }
+      uint32_t res[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        res[q] = tc_recombine(acc[0][q], acc[1][q], acc[2][q], acc[3][q], acc[4][q], acc[5][q], acc[6][q]);
+      // (row g, out 2 tig), (row g, 2 tig + 1), (row g + 8, 2 tig), (row g + 8, 2 tig + 1) of this block of 8 outputs
+      uint32_t* w0 = dst + (mt * 16 + g) * 28 + ob * 8 + tig * 2;
+      *reinterpret_cast<uint2*>(w0) = make_uint2(res[0], res[1]);
+      *reinterpret_cast<uint2*>(w0 + 8 * 28) = make_uint2(res[2], res[3]);
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t shoup_mul(uint32_t x, uint32_t dn, uint32_t dq) {   // x * d mod P, d constant
+  const uint32_t q = __umulhi(x, dq);
+  const uint32_t r = x * dn - q * P;
+  return umin32(r, r - P);
+}
+
+template <int MODE>
+__device__ __forceinline__ void p2_permute_tc(uint32_t (&c)[24], uint32_t* bufv, uint32_t* bufx, int lane) {
+  m_ext<MODE>(c);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) full_round<MODE>(c, r);
+  // ---- partial rounds. bufv keeps the state at their start (elements 1..23 are only needed again at the very end, so
+  // they do not occupy registers in between); bufx carries A, then s, then M2 s.
+  uint4* vrow = reinterpret_cast<uint4*>(bufv + lane * 28);
+  uint4* xrow = reinterpret_cast<uint4*>(bufx + lane * 28);
+#pragma unroll
+  for (int j = 0; j < 6; j++) vrow[j] = make_uint4(c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]);
+  __syncwarp();
+  tc_matvec<MODE>(bufx, bufv, g_p2_bfrag[0], lane);          // bufx[lane][r] = A_r, r < 21
+  uint32_t s[21];
+  uint32_t x0 = c[0];
+#pragma unroll
+  for (int r = 0; r < 21; r++) {
+    const uint32_t z = sbox7_rc<MODE>(x0, c_rc_partial[r]);
+    uint32_t sr = fp_add(z, bufx[lane * 28 + r]);
+    if (r > 0) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < r; j++) {
+        asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(s[j]), "r"(c_Dm[r - 1 - j]));
+        if ((j & 1) == 1 || j == r - 1) hi = umin32(hi, hi - P);
+      }
+      sr = fp_add(sr, mont_reduce(((uint64_t)hi << 32) | lo));
+    }
+    s[r] = sr;
+    x0 = fp_add(sr, shoup_mul(z, c_diag_n[0], c_diag_q[0]));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 5; j++) xrow[j] = make_uint4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+  xrow[5] = make_uint4(s[20], 0u, 0u, 0u);
+  __syncwarp();
+  tc_matvec<MODE>(bufx, bufx, g_p2_bfrag[1], lane);          // bufx[lane][i] = sum_j d_i^(20-j) s_j, 1 <= i < 24
+  c[0] = x0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const uint4 o = xrow[j], v = vrow[j];
+    const uint32_t ov[4] = {o.x, o.y, o.z, o.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int i = 4 * j + q;
+      if (i > 0) c[i] = fp_add(ov[q], shoup_mul(vv[q], c_d21_n[i], c_d21_q[i]));
+    }
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int r = 4; r < 8; r++) full_round<MODE>(c, r);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) p2_hash_rows_tc_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix,
+                                                            size_t rows, uint32_t cols) {
+  __shared__ __align__(16) uint32_t sbuf[4][2][32 * 28];
+  const int lane = threadIdx.x & 31;
+  uint32_t* bufv = sbuf[threadIdx.x >> 5][0];
+  uint32_t* bufx = sbuf[threadIdx.x >> 5][1];
+  const size_t row_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t row = row_raw < rows ? row_raw : rows - 1;      // every lane stays in the warp-wide MMAs
+  uint32_t c[24];
+#pragma unroll
+  for (int i = 0; i < 24; i++) c[i] = 0;
+  uint32_t done = 0;
+  do {
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = (done + i < cols) ? matrix[(size_t)(done + i) * rows + row] : 0u;
+    p2_permute_tc<MODE>(c, bufv, bufx, lane);
+    done += 16;
+  } while (done < cols);
+  if (row_raw < rows) {
+    uint4* o = reinterpret_cast<uint4*>(out + row * 8);
+    o[0] = make_uint4(c[0], c[1], c[2], c[3]);
+    o[1] = make_uint4(c[4], c[5], c[6], c[7]);
+  }
+}
+
 __device__ __forceinline__ void load_pair(uint32_t (&c)[24], const uint32_t* __restrict__ in) {
   const uint4* p = reinterpret_cast<const uint4*>(in);
   uint4 a = p[0], b = p[1], d = p[2], e = p[3];
@@ -375,6 +551,54 @@ void r0_poseidon2_init(Ctx* c) {
   const uint32_t one = 1, zero = 0;
   R0_CUDA(cudaMemcpyToSymbolAsync(c_one, &one, sizeof(one), 0, cudaMemcpyHostToDevice, c->stream));
   R0_CUDA(cudaMemcpyToSymbolAsync(c_zero, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, c->stream));
+  // tables of the tensor-core partial rounds (p2_hash_rows_tc_kernel)
+  {
+    auto mulmod = [](uint64_t a, uint64_t b) { return (uint32_t)(a * b % P); };
+    auto powmod = [&](uint32_t b, uint32_t e) {
+      uint32_t r = 1;
+      for (uint32_t k = 0; k < e; k++) r = mulmod(r, b);
+      return r;
+    };
+    const uint32_t R32 = (uint32_t)((uint64_t(1) << 32) % P);
+    uint32_t Dm[20], d21n[24], d21q[24];
+    for (int k = 0; k < 20; k++) {
+      uint64_t acc = 0;
+      for (int i = 1; i < 24; i++) acc += powmod(R0_P2_DIAG[i], k);
+      Dm[k] = mulmod(acc % P, R32);
+    }
+    for (int i = 0; i < 24; i++) {
+      d21n[i] = powmod(R0_P2_DIAG[i], 21);
+      d21q[i] = (uint32_t)(((uint64_t)d21n[i] << 32) / P);
+    }
+    // C[matrix][output n][input element k], already multiplied by 2^32 mod P
+    static uint32_t C[2][24][24];
+    memset(C, 0, sizeof(C));
+    for (int r = 0; r < 21; r++)
+      for (int i = 1; i < 24; i++) C[0][r][i] = mulmod(powmod(R0_P2_DIAG[i], r), R32);
+    for (int i = 1; i < 24; i++)
+      for (int j = 0; j < 21; j++) C[1][i][j] = mulmod(powmod(R0_P2_DIAG[i], 20 - j), R32);
+    static uint2 frag[2][63 * 32];
+    for (int mtx = 0; mtx < 2; mtx++)
+      for (int ob = 0; ob < 3; ob++)
+        for (int pos = 0; pos < 7; pos++)
+          for (int kt = 0; kt < 3; kt++)
+            for (int lane = 0; lane < 32; lane++) {
+              const int g = lane >> 2, tig = lane & 3;
+              uint32_t b[2] = {0, 0};
+              for (int half = 0; half < 2; half++) {
+                const uint32_t cst = C[mtx][ob * 8 + g][kt * 8 + half * 4 + tig];
+                for (int l = 0; l < 4; l++) {
+                  const int m = pos - l;     // limb of the constant that meets limb l of the value at position pos
+                  if (m >= 0 && m < 4) b[half] |= ((cst >> (8 * m)) & 0xffu) << (8 * l);
+                }
+              }
+              frag[mtx][((ob * 7 + pos) * 3 + kt) * 32 + lane] = make_uint2(b[0], b[1]);
+            }
+    R0_CUDA(cudaMemcpyToSymbolAsync(c_Dm, Dm, sizeof(Dm), 0, cudaMemcpyHostToDevice, c->stream));
+    R0_CUDA(cudaMemcpyToSymbolAsync(c_d21_n, d21n, sizeof(d21n), 0, cudaMemcpyHostToDevice, c->stream));
+    R0_CUDA(cudaMemcpyToSymbolAsync(c_d21_q, d21q, sizeof(d21q), 0, cudaMemcpyHostToDevice, c->stream));
+    R0_CUDA(cudaMemcpyToSymbolAsync(g_p2_bfrag, frag, sizeof(frag), 0, cudaMemcpyHostToDevice, c->stream));
+  }
   R0_CUDA(cudaStreamSynchronize(c->stream));
 }
 
@@ -405,6 +629,7 @@ void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows,
       case 3: p2_hash_rows2_kernel<M, 6><<<g2, 128, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
       case 4: p2_hash_rows2_kernel<M, 8><<<g2, 128, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
       case 5: p2_hash_rows_occ_kernel<M, 7><<<grid, 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
+      case 6: p2_hash_rows_tc_kernel<M><<<(unsigned)((rows + 127) / 128), 128, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
       default: throw std::invalid_argument("R0B200_P2_VARIANT: unknown variant");
     }
     count_launch(c);

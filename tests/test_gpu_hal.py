@@ -218,6 +218,31 @@ def test_hash_rows_poseidon2(hal, rows, cols):
     assert np.array_equal(out.view(), O.hash_rows(O.POSEIDON2, m, rows))
 
 
+def test_hash_rows_tensor_core_variant():
+    # poseidon2.cu's opt-in kernel that runs the 21 partial rounds' linear algebra as u8 IMMA products
+    # (R0B200_P2_VARIANT=6; the switch is read once per process, hence the subprocess): same digests as the oracle,
+    # incl. ragged last sponge blocks and a row count that is not a multiple of the warp size
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import oracle_lib as O\n"
+        "from risc0_b200 import B200Hal\n"
+        "hal = B200Hal(0, 'poseidon2')\n"
+        "for rows, cols in [(64, 16), (256, 1), (1024, 37), (4096, 211), (96, 103), (10, 64)]:\n"
+        "    rng = np.random.default_rng(rows * 1000 + cols)\n"
+        "    m = O.rand_elems(rng, rows * cols)\n"
+        "    out = hal.alloc_digest('out', rows)\n"
+        "    hal.hash_rows(out, hal.copy_from_elem('m', m))\n"
+        "    assert np.array_equal(out.view(), O.hash_rows(O.POSEIDON2, m, rows)), (rows, cols)\n"
+        "hal.close(); print('tc variant ok')\n" % (os.path.dirname(here), here))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, R0B200_P2_VARIANT="6"), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "tc variant ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("rows,cols", [(1, 16), (3, 32), (10, 64), (1000, 17), (257, 211), (4, 0)])
 def test_hash_rows_sha(hal_sha, rows, cols):
     rng = rng_for("rowssha", rows, cols)
