@@ -447,6 +447,10 @@ def main():
     # kernel families: the generated eval_check part kernels are one family ("eval_check" brackets them)
     families = {k: v for k, v in phases.items() if not k.startswith("eval_check_p")}
     top = max(families.items(), key=lambda kv: kv[1]["ms"])
+    # eval_check and hash_rows are within 0.2 % of each other since the per-part tuning: keep the reported family stable
+    # (eval_check, the one VERDICT names) unless another one leads by more than 2 %
+    if "eval_check" in families and families["eval_check"]["ms"] >= 0.98 * top[1]["ms"]:
+        top = ("eval_check", families["eval_check"])
     tname, t = top
     nlaunch = t["n"]
     stats = {}
@@ -489,11 +493,20 @@ def main():
                  "wide_multiplies_per_point": stats["wide_multiplies"], "reductions_per_point": stats["reductions"],
                  "fma_cycles_needed": need, "smsp_cycles_available": smsp_cycles, "frac": need / smsp_cycles}
     elif tname == "hash_rows":
-        perms = (4 << po2) * 23 * t["n"]                           # 1 + 14 + 7 + 1 sponge blocks per domain row
+        perms = (4 << po2) * 23 * args.steps                       # 1 + 14 + 7 + 1 sponge blocks per domain row (FRI trees: +1.4 %)
         need = perms * 12.5e3 / 32.0                               # 852 x 10 + 504 x 8 fma-pipe cycles per permutation and warp lane group
         int32 = {"bound": "fma pipe (Poseidon2: 852 Montgomery + 504 Shoup products per permutation)", "permutations": perms,
                  "Gperm_per_s": perms / (t["ms"] * 1e-3) / 1e9, "fma_cycles_needed": need, "smsp_cycles_available": smsp_cycles,
                  "frac": need / smsp_cycles}
+    # the other big family, same algorithmic-bytes basis (both are INT32-bound)
+    other = "hash_rows" if tname == "eval_check" else "eval_check"
+    roofline_other = None
+    if other in families and families[other]["ms"] > 0:
+        o = families[other]
+        roofline_other = {"kernel": other, "achieved": o["bytes"] / (o["ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": o["bytes"] / (o["ms"] * 1e-3) / 1e9 / peak, "share_of_step": o["ms"] / ms_one,
+                          "Gperm_per_s": ((4 << po2) * 23 * args.steps) / (o["ms"] * 1e-3) / 1e9 if other == "hash_rows" else None}
+    peak_bytes = sum(h.bytes_peak() for h in hals)     # before the side runs (po2 = 22 needs 38 GB on its own)
     cpu_baseline = None
     extras = None
     if rank == 0 and world == 1:
@@ -535,10 +548,10 @@ def main():
                                     "with r0b200_segment_upload on its worker's copy stream, one step ahead of the proof (depth 2 per "
                                     "worker, %d workers per GPU), and reads the seal + globals back; the witness matrices never exist "
                                     "on the host" % W},
-                "gpu_launches": int(launches), "roofline": roofline, "int32_roofline": int32, "cpu_baseline": cpu_baseline,
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_other": roofline_other, "int32_roofline": int32, "cpu_baseline": cpu_baseline,
                 "ms_per_step_one_in_flight": ms_one / args.steps,
                 "phase_ms_per_step": phase_ms, "phase_alg_GBps": phase_gbs, "clocks": sampler.result(),
-                "seal_words": int(len(seal)), "peak_device_bytes": sum(h.bytes_peak() for h in hals), "configs": extras}
+                "seal_words": int(len(seal)), "peak_device_bytes": peak_bytes, "configs": extras}
         emit(line)
     for h in hals[1:]:
         h.close()
