@@ -301,9 +301,12 @@ __global__ void __launch_bounds__(128, MINB) p2_hash_rows2_kernel(uint32_t* __re
 // opt-in. It removes 5.2 k of the 29.9 k integer pipe-cycles of a permutation, but as built its phases do not overlap
 // well enough: removing in turn the 252 IMMAs (+ their B-fragment loads, 64 KB of L1 traffic per warp and
 // permutation), the 21-step recurrence and the 48 recombinations brings 8.75 ms down to 6.46 / 6.94 / 7.38 ms, all
-// three to 5.05 ms (the full rounds). IMMA.16832 issues once per 8.4 cycles per sub-partition (1958 MAC/clk/SM,
-// tools/ubench/mma_u8.cu). Next steps if picked up again: B fragments shared by both row tiles, limb-major K (16
-// instead of 21 MMAs per output block), 64 registers for 32 warps per SM.
+// three to 5.05 ms (the full rounds). The reason is in tools/ubench/mma_u8.cu (profiles/r2_mma_u8_rates.log):
+// IMMA.16832 issues once per 8.4 cycles per sub-partition (1953 MAC/clk/SM) and does NOT overlap the integer pipes - an
+// IMMA and an IMAD.WIDE per iteration take 14.9 cycles, more than the 8.4 + 4.8 they take alone. The 252 IMMAs of a
+// permutation therefore cost 2.1 k issue cycles per warp to save 2.6 k cycles of integer work: a wash through
+// mma.sync. Only the asynchronous path (tcgen05.mma issued by one thread, accumulators in TMEM, operands staged by
+// TMA) could run beside the S-box arithmetic; that is the version worth building next.
 __device__ __forceinline__ void imma_u8(int (&c)[4], const uint32_t (&a)[4], const uint2 b) {
   asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])

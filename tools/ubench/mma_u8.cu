@@ -47,9 +47,9 @@ float run(uint32_t* out, int sms) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  k<MODE><<<sms * 2, 1024>>>(out, 12345u);
+  k<MODE><<<sms * 8, 256>>>(out, 12345u);
   cudaEventRecord(e0);
-  k<MODE><<<sms * 2, 1024>>>(out, 12345u);
+  k<MODE><<<sms * 8, 256>>>(out, 12345u);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms;
@@ -64,9 +64,9 @@ int main() {
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
   const double ghz = khz / 1e6;
   uint32_t* out;
-  cudaMalloc(&out, (size_t)p.multiProcessorCount * 2 * 1024 * 4);
+  cudaMalloc(&out, (size_t)p.multiProcessorCount * 8 * 256 * 4);
   const int sms = p.multiProcessorCount;
-  const double warps = sms * 2 * 32.0, per_warp = ITERS * 8.0;
+  const double warps = sms * 8 * 8.0, per_warp = ITERS * 8.0;
   const float t0 = run<0>(out, sms), t1 = run<1>(out, sms), t2 = run<2>(out, sms);
   auto cyc = [&](float ms) { return ms * 1e-3 * ghz * 1e9 * sms * 4 / (warps * per_warp); };   // SMSP cycles per warp-level op
   printf("%s: mma.m16n8k32.u8 alone %.3f ms = %.2f cycles per MMA per sub-partition (%.0f int8 MAC/clk/SM)\n", p.name, t0, cyc(t0),
