@@ -128,12 +128,7 @@ bool r0_bit_reverse_tma(Ctx* c, uint32_t* io, size_t count, int k) {
   if (off || k < 10 || (reinterpret_cast<uintptr_t>(io) & 15) != 0) return false;
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
-  static bool attr_set = false;
-  const int smem_bytes = 4 * TILE_BYTES + 1024;
-  if (!attr_set) {
-    R0_CUDA(cudaFuncSetAttribute(bit_reverse_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  const int smem_bytes = 4 * TILE_BYTES + 1024;   // 17 KB: under the 48 KB that needs no opt-in
   const int midbits = k - 10;
   for (size_t c0 = 0; c0 < count; c0 += 65535) {
     const size_t nc = count - c0 < 65535 ? count - c0 : 65535;
