@@ -42,6 +42,9 @@
 #define R0_NTT_LGT_SMALL 3  // log2 of the adjacent columns per strided tile for k1 <= 10
 #endif
 
+#ifndef R0_NTT_ADDITIVE
+#define R0_NTT_ADDITIVE 1   // twiddle products reduced in the additive Montgomery form (see ntt_mul): -2.6 % on iNTT and LDE (profiles/r2_ntt_sweep5.log)
+#endif
 #ifndef R0_NTT_SHOUP
 #define R0_NTT_SHOUP 0   // table twiddles as (w, floor(w 2^32 / P)) pairs: IMAD.HI + 2 IMAD + VIADDMNMX per product
 #endif
@@ -112,6 +115,15 @@ __device__ __forceinline__ uint32_t bf_sub(uint32_t x, uint32_t y) {
 // Montgomery product as fp_mul (fp.cuh), with the same control over the subtraction's pipe
 __device__ __forceinline__ uint32_t ntt_mul(uint32_t a, uint32_t b) {
   const uint64_t t = (uint64_t)a * b;
+#if R0_NTT_ADDITIVE
+  // additive reduction: t + (lo(t) * -P^-1) * P has a zero low word; with ONE canonical factor t < 2^32 P, so the sum
+  // stays below 2^33 P < 2^64 and its high word is the product in [0, 2P). The carry-chained pair becomes one IMAD.WIDE
+  // with a 64-bit addend: IMAD.WIDE, IMAD, IMAD.WIDE, VIADDMNMX - one alu-pipe instruction less than the subtractive form.
+  uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+  const uint32_t mm = lo * MONT_NINV;
+  asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(mm), "r"(P));
+  return umin32(hi, hi - P);
+#endif
   const uint32_t m = (uint32_t)t * MONT_PINV;
   const uint32_t h = __umulhi(m, P);
   const uint32_t r = (R0_NTT_IADD3 & 4) ? (uint32_t)(t >> 32) - h + c_ntt_zero : (uint32_t)(t >> 32) - h;

@@ -665,6 +665,7 @@ class Ptx:
         self.first_wide = os.environ.get("EVAL_FIRST_WIDE", "1") == "1"
         self.mshift = os.environ.get("EVAL_MSHIFT", "0") == "1"
         self.pin_adds = os.environ.get("EVAL_PIN", "0") == "1"
+        self.additive = part_opt(name, "EVAL_ADDITIVE", "0") == "1"
         self.bases = {}
 
     def t(self):
@@ -745,6 +746,18 @@ class Ptx:
         # subtractive Montgomery reduction (csrc/fp.cuh mont_reduce): m = lo * P^-1; r = hi - hi(m * P) in (-P, P);
         # canonical = min.u32(r, r + P). No carry chain, 4 instructions.
         m, h, r, r2 = self.t(), self.t(), self.t(), self.t()
+        if self.additive:
+            # additive form: m = lo * (-P^-1); (lo, hi) + m * P has a zero low word, its high word is the result in
+            # [0, 2P) (the accumulator is < P 2^32 and m P < 2^32 P, so the sum stays under 2^64). The carry-chained pair
+            # folds into ONE IMAD.WIDE with a 64-bit addend: IMAD + IMAD.WIDE + VIADDMNMX instead of IMAD + IMAD.HI +
+            # IADD3 + VIADDMNMX - one alu-pipe instruction less per reduction.
+            z = self.t()
+            self.emit("mul.lo.u32 %s, %s, %d;" % (m, lo, NINV))
+            self.emit("mad.lo.cc.u32 %s, %s, %d, %s;" % (z, m, P, lo))
+            self.emit("madc.hi.u32 %s, %s, %d, %s;" % (r, m, P, hi))
+            self.emit("add.u32 %s, %s, %d;" % (r2, r, (1 << 32) - P))
+            self.emit("min.u32 %s, %s, %s;" % (dst, r, r2))
+            return
         if self.mshift:
             # m = lo * P^-1 with P^-1 = 1 + 2^27 + 2^31 as two shifts and one three-input add on the alu pipe (which is
             # half idle in these kernels) instead of an IMAD on the saturated fma pipe. The shift amounts are opaque

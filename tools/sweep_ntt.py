@@ -24,15 +24,11 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 # groups. Sweep 2 (r1_ntt_sweep2.log): strided-pass tile width x block size: 8 columns x 256 threads stays.
 # Sweep 3 (r1_ntt_sweep3.log): Shoup twiddle products / butterfly adds as IMAD: no effect (ptxas already emits IMAD.IADD).
 # Sweep 4: the opposite direction - keep adds on the alu pipe (three-input IADD3), with and without Shoup products.
+# Sweep 5 (r2_ntt_sweep5.log): additive Montgomery reduction in the twiddle products.
 VARIANTS = {
     "base": [],
-    "iadd1": ["-DR0_NTT_IADD3=1"],
-    "iadd2": ["-DR0_NTT_IADD3=2"],
-    "iadd3": ["-DR0_NTT_IADD3=3"],
-    "iadd4": ["-DR0_NTT_IADD3=4"],
-    "iadd7": ["-DR0_NTT_IADD3=7"],
-    "shoup_iadd3": ["-DR0_NTT_SHOUP=1", "-DR0_NTT_IADD3=3"],
-    "shoup_iadd7": ["-DR0_NTT_SHOUP=1", "-DR0_NTT_IADD3=7"],
+    "additive": ["-DR0_NTT_ADDITIVE=1"],
+    "additive_iadd3": ["-DR0_NTT_ADDITIVE=1", "-DR0_NTT_IADD3=3"],
 }
 
 # run-time points tried for every variant (the first one is the library default)
