@@ -79,6 +79,7 @@ __device__ __forceinline__ uint32_t sbox7(uint32_t x) {
 //   bit 7: EVERY addition (and the Montgomery subtraction) pinned to the alu pipe as a three-input IADD3
 //   bit 8: bits 0-5 choose between the two PINNED forms (set = three-input IADD3, clear = IMAD x*1+y); without it a
 //          set bit only writes a plain add, which ptxas re-issues as IMAD.IADD / IADD3 to balance instruction counts
+//   bit 9: the S-box products in the additive (unsigned) Montgomery form, see sbox7_additive
 //   bit 6: round constants enter the S-box unreduced: x = c + rc - P in (-P, P) is a legal signed operand of the x^7
 //          chain, so the modular add (IADD3 + VIADDMNMX) becomes one IADD3
 // The best mask is measured (tools/bench_hash.py --mode, profiles/r2_poseidon2_modes.log); R0B200_P2_MODE overrides it.
@@ -89,8 +90,29 @@ __device__ __forceinline__ uint32_t add_m(uint32_t a, uint32_t b) {
   if (MODE & (1 << BIT)) return fp_add(a, b);
   return fp_add_fma(a, b);
 }
+// Unsigned Montgomery product in the additive form: t + (lo(t) * -P^-1) * P has a zero low word and its high word is
+// a * b / 2^32 + (less than) P. IMAD.WIDE, IMAD, IMAD.WIDE with a 64-bit addend: no subtraction on the alu pipe.
+__device__ __forceinline__ uint32_t mul_additive(uint32_t a, uint32_t b) {
+  const uint64_t t = (uint64_t)a * b;
+  uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+  const uint32_t m = lo * MONT_NINV;
+  asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(m), "r"(P));
+  return hi;
+}
+// x^7 with the additive products (MODE bit 9). Bounds, with c = P / 2^32 = 0.469 and x < P: x2 < (c + 1) P = 1.47 P is
+// made canonical; x4 = x2^2 < 1.47 P; x6 = x4 x2 < (1.47 c + 1) P = 1.69 P; x7 = x6 x < (1.69 c + 1) P = 1.79 P < 2^32.
+__device__ __forceinline__ uint32_t sbox7_additive(uint32_t x) {
+  uint32_t x2 = mul_additive(x, x);
+  x2 = umin32(x2, x2 - P);
+  const uint32_t x4 = mul_additive(x2, x2);
+  const uint32_t x6 = mul_additive(x4, x2);
+  const uint32_t r = mul_additive(x6, x);
+  return umin32(r, r - P);
+}
+
 template <int MODE>
 __device__ __forceinline__ uint32_t sbox7_rc(uint32_t x, uint32_t rc) {
+  if (MODE & 512) return sbox7_additive(fp_add(x, rc));
   if (MODE & 64) {
     int32_t x1 = (int32_t)(x + rc - P);   // in (-P, P)
     if (MODE & 384) asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(x1) : "r"(x), "r"(rc), "r"(c_zero - P));
@@ -179,7 +201,10 @@ __device__ __forceinline__ void p2_permute_m(uint32_t (&c)[24]) {
   for (int r = 4; r < 8; r++) full_round<MODE>(c, r);
 }
 #ifndef R0_P2_DEFAULT_MODE
-#define R0_P2_DEFAULT_MODE 32   // round-1 schedule: everything on the fma pipe except the partial round's "+ sum"
+// 563 = additive S-box products (bit 9) + plain adds (ptxas picks the pipe) in both M4 stages, the partial rounds' sum
+// tree and "+ sum" (bits 0, 1, 4, 5), the rest as IMAD: 2.26 Gperm/s against 2.15 for round 1's schedule (32), measured
+// over 40 masks (profiles/r2_poseidon2_modes*.log)
+#define R0_P2_DEFAULT_MODE 563
 #endif
 
 // out[row] = sponge over matrix[j*rows + row], j < cols (overwrite mode, zero-filled tail, empty input = one permute)
@@ -612,8 +637,8 @@ static int p2_mode() {
 // the fold kernels are compiled for the default schedule and the two all-alu reference points of the mode experiment
 #define P2_FOLD_DISPATCH(CALL)                         \
   switch (p2_mode()) {                                 \
+    case 32: { constexpr int M = 32; CALL; } break;    \
     case 128: { constexpr int M = 128; CALL; } break;  \
-    case 192: { constexpr int M = 192; CALL; } break;  \
     default: { constexpr int M = R0_P2_DEFAULT_MODE; CALL; } break; \
   }
 
@@ -641,8 +666,8 @@ void r0_p2_hash_rows(Ctx* c, uint32_t* out, const uint32_t* matrix, size_t rows,
   }
 #define P2_ROWS(M) case M: p2_hash_rows_kernel<M><<<grid, 256, 0, c->stream>>>(out, matrix, rows, (uint32_t)cols); break;
   switch (p2_mode()) {
-    P2_ROWS(0) P2_ROWS(32) P2_ROWS(63) P2_ROWS(64) P2_ROWS(96) P2_ROWS(120) P2_ROWS(127) P2_ROWS(128) P2_ROWS(192)
-    P2_ROWS(288) P2_ROWS(290) P2_ROWS(300) P2_ROWS(304) P2_ROWS(364) P2_ROWS(372)
+    P2_ROWS(0) P2_ROWS(32) P2_ROWS(63) P2_ROWS(64) P2_ROWS(127) P2_ROWS(128) P2_ROWS(192) P2_ROWS(288) P2_ROWS(304)
+    P2_ROWS(372) P2_ROWS(512) P2_ROWS(544) P2_ROWS(546) P2_ROWS(563) P2_ROWS(575)
     default: throw std::invalid_argument("R0B200_P2_MODE: mask not compiled in");
   }
 #undef P2_ROWS
