@@ -30,17 +30,17 @@ __device__ uint2 g_p2_bfrag[2][63 * 32];
 __constant__ uint32_t c_one;  // = 1, opaque to the compiler: a * c_one + b is an IMAD, i.e. an add on the fma pipe
 __constant__ uint32_t c_zero;  // = 0, opaque to the compiler: a + b + c_zero is a genuine three-input IADD3 (alu pipe)
 
-// The permutation is bound by the alu pipe (every modular add / product ends in a VIADDMNMX there), while the fma pipe
-// is half idle; adds in the linear layer are therefore issued as IMAD (x * 1 + y) to balance the two pipes.
+// An addition pinned to the fma pipe: x * 1 + y with a 1 the compiler cannot see through is an IMAD. Which groups of
+// linear-layer additions take this form is the MODE mask below; it was chosen by measurement.
 __device__ __forceinline__ uint32_t fp_add_fma(uint32_t a, uint32_t b) {
   uint32_t r = a * c_one + b;
   return umin32(r, r - P);
 }
 
-// ptxas balances INSTRUCTION COUNTS between the two integer pipes on its own: it rewrites plain two-input adds as
-// IMAD.IADD (fma pipe) or LEA / IADD3 (alu pipe) whichever way they are written in C. It does not know that
-// IMAD.WIDE / IMAD.HI hold the fma pipe for 4 cycles, so it leaves that pipe over-committed. A three-input add cannot
-// become an IMAD, so this form pins an addition to the alu pipe.
+// ptxas balances the two integer pipes on its own: it rewrites plain two-input adds as IMAD.IADD (fma pipe) or
+// LEA / IADD3 / VIADD (alu pipe) whichever way they are written in C, with a machine model in which IMAD.WIDE / IMAD.HI
+// hold the fma pipe 4 cycles and the alu pipe 2 (measured: profiles/r2_int_pipe_rates.log). A three-input add cannot
+// become an IMAD, so this form pins an addition to the alu pipe (modes 128 - 372: never faster than ptxas' own split).
 __device__ __forceinline__ uint32_t fp_add_alu(uint32_t a, uint32_t b) {
   uint32_t r;   // inline PTX so that the front end cannot share (a + c_zero) between sums and leave two-input adds behind
   asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(r) : "r"(a), "r"(b), "r"(c_zero));
