@@ -10,7 +10,11 @@ namespace {   // internal linkage: both step translation units instantiate the s
 }  // namespace
 
 #ifndef WG_MIN_BLOCKS
-#define WG_MIN_BLOCKS 6   // measured at po2 = 20 (tools/witgen_variants.sh): 1 -> 4.30 ms, 6 -> 2.54, 8 -> 2.31, 10 -> 2.21; but under the 64- / 48-register caps of 8 / 10 the -O1 build mis-computes the all-instruction guest (tests/test_gpu_witgen.py [all_insn], eqz failure) while the host build of the same text is clean under ASan + UBSan: 6 is the tightest setting the whole suite passes with
+#define WG_MIN_BLOCKS 8   // measured at po2 = 20 (tools/witgen_const_check.sh, profiles/r2_witgen_out_params.log): 6 -> 2.66 ms, 8 -> 2.42, 10 -> 2.47.
+// History: with aggregates returned BY VALUE from the non-inlined step functions, the 8 / 10 block builds (64 / 48
+// registers) and the ptxas -O3 build mis-computed the all-instruction guest - bits of the first ToBits_16 result changed
+// across the second call inside BitwiseAndU16. The generator now hands such results back through a reference
+// (tools/gen_witgen.py returns_by_out_param); every one of those builds passes the whole witgen suite since.
 #endif
 __global__ void __launch_bounds__(128, WG_MIN_BLOCKS) k_step_exec(const WShared* s, const uint32_t* order, uint32_t begin, uint32_t count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -59,7 +59,7 @@ def test_results_in_order_any_S_over_G(S, G):
 
 def test_uneven_segments_balance_across_devices():
     # one heavy segment (40x) and 20 light ones on 2 devices: the free device takes the light ones meanwhile
-    c = FakeCluster(prove_s=0.005)
+    c = FakeCluster(prove_s=0.01)
     segs = [{"i": 0, "w": 40}] + [{"i": i} for i in range(1, 21)]
     t0 = time.perf_counter()
     res = c.scheduler([0, 1]).run(segs)
@@ -67,17 +67,21 @@ def test_uneven_segments_balance_across_devices():
     heavy_dev = res[0].device
     light_on_other = sum(1 for r in res[1:] if r.device != heavy_dev)
     assert light_on_other >= 15
-    assert wall < 0.005 * (40 + 20) * 0.9       # clearly better than one device doing everything
+    assert wall < 0.01 * (40 + 20) * 0.9        # clearly better than one device doing everything
 
 
 def test_upload_runs_one_segment_ahead_of_prove_per_device():
-    c = FakeCluster(prove_s=0.02)
-    c.scheduler([0]).run([{"i": i} for i in range(4)])
-    ev = [(w, i) for (w, d, i) in c.events if w in ("upload", "prove")]
-    # in steady state segment i + 1 is uploaded before segment i has been proved (the very first segment may be proved
-    # before the second one has left preflight)
-    for i in range(1, 3):
-        assert ev.index(("upload", i + 1)) < ev.index(("prove", i))
+    c = FakeCluster(prove_s=0.05)
+    c.scheduler([0]).run([{"i": i} for i in range(5)])
+    ev = [w for (w, d, i) in c.events if w in ("upload", "prove")]
+    uploads = [k for k, w in enumerate(ev) if w == "upload"]
+    proves = [k for k, w in enumerate(ev) if w == "prove"]
+    assert len(uploads) == len(proves) == 5
+    # depth 2 in steady state: the (n + 1)-th upload is started before the n-th proof has finished. Counted by position,
+    # not by segment index - two preflight workers may hand segments over out of order - and from n = 1 on: the very first
+    # segment may be proved before the second one has left preflight.
+    for n in range(1, 4):
+        assert uploads[n + 1] < proves[n]
 
 
 def test_preflight_look_ahead_is_bounded():

@@ -25,6 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.join(HERE, "..")
 P = 15 * 2**27 + 1
 BUF_IDS = {"data": 0, "accum": 1, "global": 2, "mix": 3}
+OUT_PARAMS = os.environ.get("WITGEN_OUT_PARAMS", "1") == "1"   # non-inlined functions return aggregates through a reference
 INLINE_LIMIT = int(os.environ.get("WITGEN_INLINE_LIMIT", "1500"))   # JSON size of a body below which it is force-inlined
 
 
@@ -39,6 +40,7 @@ class Gen:
         self.funcs = ir["funcs"]
         self.flat_cache = {}
         self.sites = []
+        self.const_tables = {}     # tuple of Montgomery words -> table name (constant arrays hoisted out of the functions)
         self.layout_base = {}
         self.layout_cols = []
         for name, lay in ir["layouts"].items():
@@ -162,6 +164,17 @@ class Gen:
             return "bind_layout(%du, %s)" % (self.layout_base[name], buf), self.ir["layouts"][name]["type"]
         raise ValueError("not a layout expression: %r" % (e,))
 
+    def const_table(self, e):
+        """name of the namespace-scope table for an array literal whose elements are all field constants, else None.
+        Such literals used to be emitted as temporaries (`Val30Array{{...}}[i]`): an array built on the thread's stack
+        and indexed dynamically; they now live in constant memory (30 stores + a local load less per use)."""
+        if e[0] != "array" or not e[2] or any(x[0] != "val" for x in e[2]):
+            return None
+        key = tuple(mont(x[1]) for x in e[2])
+        if key not in self.const_tables:
+            self.const_tables[key] = "kConstArr%d" % len(self.const_tables)
+        return self.const_tables[key]
+
     # ---- value expressions
     def expr(self, e, env):
         k = e[0]
@@ -176,6 +189,9 @@ class Gen:
         if k == "fld":
             return "%s.%s" % (self.expr(e[1], env), e[2])
         if k == "idx":
+            t = self.const_table(e[1])
+            if t is not None:     # constant array indexed in place: a load from the hoisted table, no local array
+                return "Val::raw(%s[%s])" % (t, self.expr(e[2], env))
             return "%s[%s]" % (self.expr(e[1], env), self.expr(e[2], env))
         if k == "bin":
             return "(%s %s %s)" % (self.expr(e[2], env), e[1], self.expr(e[3], env))
@@ -203,6 +219,14 @@ class Gen:
                 for (pty, _), a in zip(params, e[2]):
                     args.append(self.lay(a, env)[0] if pty.startswith("BoundLayout<") else self.expr(a, env))
                 return "%s(ctx%s)" % (name, "".join(", " + a for a in args))
+            if name == "inv_0" and len(e[2]) == 1 and e[2][0][0] == "idx" and self.const_table(e[2][0][1]) is not None:
+                # the inverse of an element of a constant array (ToBits: inv(2^i) for every bit of every decomposed
+                # value): a second constant table instead of a ~45-product field inversion per use
+                src = e[2][0][1]
+                key = tuple(mont(pow(x[1] % P, P - 2, P)) for x in src[2])
+                if key not in self.const_tables:
+                    self.const_tables[key] = "kConstArr%d" % len(self.const_tables)
+                return "Val::raw(%s[%s])" % (self.const_tables[key], self.expr(e[2][0][2], env))
             return "%s(%s)" % (name, ", ".join(self.expr(a, env) for a in e[2]))
         raise ValueError("unhandled expression %r" % (e[:2],))
 
@@ -257,6 +281,8 @@ class Gen:
             elif k == "return":
                 if s[1] is None:
                     out.append("%sreturn;" % pad)
+                elif ret_target is not None:   # out-parameter form of a non-inlined function (see generate)
+                    out.append("%s{ %s = %s; return; }" % (pad, ret_target, self.expr(s[1], env)))
                 else:
                     out.append("%sreturn %s;" % (pad, self.expr(s[1], env)))
             elif k == "unreachable":
@@ -291,7 +317,11 @@ class Gen:
         out.append("%sauto fn%d = [&](%s) -> %s {" % (pad, t, sig, ret_ty))
         self.stmts(lam["body"], lenv, ind + 1, out)
         out.append("%s};" % pad)
-        out.append("%sconst auto arr%d = %s;" % (pad, t, self.expr(arr, env)))
+        ct = self.const_table(arr)
+        if ct is not None:
+            out.append("%sconst ConstArr arr%d{%s};" % (pad, t, ct))
+        else:
+            out.append("%sconst auto arr%d = %s;" % (pad, t, self.expr(arr, env)))
         if is_map:
             assert self.types[aty][2] == n, (aty, n)
             out.append("%s%s %s;" % (pad, self.ctype(ty), name))
@@ -302,7 +332,7 @@ class Gen:
             out.append("%sfor (uint32_t i%d = 0; i%d < %du; i%d++) %s = fn%d(%s, arr%d[i%d], %s + i%d * %du);" % (
                 pad, t, t, n, t, name, t, name, t, t, base, t, esz))
 
-    def signature(self, name):
+    def signature(self, name, out_form=False):
         f = self.funcs[name]
         ps = []
         for ty, pn in f["params"]:
@@ -311,7 +341,23 @@ class Gen:
                 ps.append("%s %s" % (c, pn))
             else:
                 ps.append("const %s& %s" % (c, pn))
+        if out_form:
+            return "void %s_o(WCtx& ctx%s, %s& ret_o)" % (name, "".join(", " + p for p in ps), self.ctype(f["ret"]))
         return "%s %s(WCtx& ctx%s)" % (self.ctype(f["ret"]), name, "".join(", " + p for p in ps))
+
+    def returns_by_out_param(self, name):
+        """A function that is a real call (not force-inlined) and returns a struct / array hands its result back through
+        a reference to the caller's variable instead of by value. By value such a result travels in the PTX call's
+        return parameter (`.param .align 4 .b8 retval0[64]` for the 16 bit registers of ToBits_16), and that is where
+        the exec kernel went wrong on the device when ptxas had to work under a tight register cap (8 / 10 blocks per
+        SM) or at -O3: BitwiseAndU16 keeps the first ToBits_16 result live across the second call, both decompositions
+        passed their own eqz checks, and the AND of the two came out with single bits of the FIRST result changed
+        (tests/test_gpu_witgen.py [all_insn]; the host build of the same text is clean under ASan / UBSan and with
+        pattern-initialised locals). With the result written through a pointer the calling convention carries only
+        scalars and pointers."""
+        f = self.funcs[name]
+        size = len(json.dumps(f["body"]))
+        return OUT_PARAMS and size > INLINE_LIMIT and self.ctype(f["ret"]) not in ("Val", "void", "uint32_t", "BL")
 
     def generate(self):
         out = ["// GENERATED by tools/gen_witgen.py from risc0_b200/circuits/rv32im_witgen.ir.json.gz - do not edit.",
@@ -343,14 +389,41 @@ class Gen:
         out.append("")
         for name in self.funcs:
             out.append("WG_FN %s;" % self.signature(name))
+            if self.returns_by_out_param(name):
+                out.append("WG_FN %s;" % self.signature(name, out_form=True))
         out.append("")
+        body = []
         for name, f in self.funcs.items():
             size = len(json.dumps(f["body"]))
             qual = "WG_INLINE" if size <= INLINE_LIMIT else "WG_NOINLINE"
-            out.append("%s %s {" % (qual, self.signature(name)))
             env = {pn: self.layout_of(ty) for ty, pn in f["params"] if ty.startswith("BoundLayout<")}
-            self.stmts(f["body"], env, 1, out)
-            out.append("}")
+            if self.returns_by_out_param(name):
+                body.append("WG_NOINLINE %s {" % self.signature(name, out_form=True))
+                self.stmts(f["body"], env, 1, body, ret_target="ret_o")
+                body.append("}")
+                body.append("WG_INLINE %s {" % self.signature(name))   # call sites stay expressions
+                body.append("  %s r;" % self.ctype(f["ret"]))
+                body.append("  %s_o(ctx%s, r);" % (name, "".join(", " + pn for _, pn in f["params"])))
+                body.append("  return r;")
+                body.append("}")
+                continue
+            body.append("%s %s {" % (qual, self.signature(name)))
+            self.stmts(f["body"], env, 1, body)
+            body.append("}")
+        # constant arrays of the step functions (Montgomery words), hoisted to constant memory
+        out.append("#if defined(__CUDACC__)")
+        out.append("#define WG_TABLE static __constant__ uint32_t")
+        out.append("#else")
+        out.append("#define WG_TABLE static const uint32_t")
+        out.append("#endif")
+        out.append("struct ConstArr {")
+        out.append("  const uint32_t* p;")
+        out.append("  WG_RT Val operator[](uint32_t i) const { return Val::raw(p[i]); }")
+        out.append("};")
+        for key, tname in self.const_tables.items():
+            out.append("WG_TABLE %s[%d] = {%s};" % (tname, len(key), ", ".join("%du" % w for w in key)))
+        out.append("")
+        out.extend(body)
         out.append("#endif  // R0_WG_TABLES_ONLY")
         out.append("")
         out.append("#ifdef R0_WG_SITE_STRINGS")
@@ -370,6 +443,9 @@ def main():
     sys.setrecursionlimit(100000)
     ir = json.load(gzip.open(a.ir))
     text = Gen(ir).generate()
+    if os.path.exists(a.o) and open(a.o).read() == text:
+        print("%s: unchanged" % a.o)   # keep the file and its time: the two step kernels need minutes to rebuild
+        return
     with open(a.o, "w") as f:
         f.write(text)
     print("%s: %d lines" % (a.o, text.count("\n")))
