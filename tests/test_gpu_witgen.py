@@ -25,6 +25,7 @@ def segments():
     out = {"loop_po2_13": PF.execute(PF.simple_loop_kernel(200), segment_po2=14)[0],
            "all_insn": PF.execute(all_insn_guest(), segment_po2=14)[0]}
     out["user_mode"] = PF.execute(PF.user_mode_guest(30), segment_po2=14)[0]
+    out["sha2"] = PF.execute(PF.sha2_guest(bytes(range(200))), segment_po2=14)[0]   # 4 blocks through the sha2 ecall
     split = PF.execute(PF.simple_loop_kernel(4000), segment_po2=13)
     out["split_first"], out["split_second"] = split[0], split[1]
     return out
@@ -40,7 +41,7 @@ def seg(name):
     return SEGS[name]
 
 
-@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second", "user_mode"])
+@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second", "user_mode", "sha2"])
 def test_device_witgen_and_accum_match_reference(hal, name):
     pf = PF.PreflightResults(seg(name), (11, 12, 13, 14))
     want_glob, want_data = W.ref_generate_witness(pf)
@@ -67,7 +68,7 @@ def test_device_witgen_reports_bad_traces(hal):
     WitnessGenerator(hal, pf)                        # the context is still usable afterwards
 
 
-@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "user_mode"])
+@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "user_mode", "sha2"])
 def test_prove_core_from_trace_bit_exact_and_valid(hal, name):
     pf = PF.PreflightResults(seg(name), (21, 22, 23, 24))
     po2 = pf.po2
