@@ -17,7 +17,7 @@ phase_of={'eval_check_rv32im (36 parts)':'eval_check','r0::p2_hash_rows_kernel':
 L=[]
 L.append('# Round 2 - ncu launch list of one whole prove_core at po2 = 20 (real loop-guest segment, witness generated on the device)\n')
 L.append('Command (after the same command had exited 0 without ncu in the same gpurun call, `tools/final_profile.sh`):\n')
-L.append('    ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2f_launches.csv python tools/profile_target.py\n')
+L.append('    ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/<tag>_launches.csv python tools/profile_target.py\n')
 L.append('Raw list: `profiles/r2_launches.csv` (%d launches = exactly one step, no warm-up proof). ncu serialises launches and runs them cold-cache: compare SHARES with the bench line\'s one-in-flight `phase_ms_per_step` (`profiles/r2_bench_n1.json`, %.1f ms per step one segment at a time), not absolutes.\n' % (n, one))
 L.append('| kernel family | launches | device ms | share | bench phase (ms, share of %.1f) |'%one)
 L.append('|---|---|---|---|---|')
