@@ -1,5 +1,15 @@
-import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+"""GPU box: run the device witness generator on the all-instruction guest (po2 = 14) and, when it fails or differs from
+the reference's compiled C++ witgen, print the mismatching cells (cycle, major / minor, column, got / want).
+
+    [R0B200_LIB=risc0_b200/lib/libr0b200_<variant>.so] python tools/dbg_witgen.py
+
+Used to localise the exec-kernel build problem described in DESIGN.md 3.6 (tools/witgen_const_check.sh)."""
+import os
+import sys
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import witgen_ref as W
 from risc0_b200 import B200Hal, preflight as PF
