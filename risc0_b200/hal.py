@@ -407,6 +407,11 @@ class WitnessGenerator:
         self.accum_buf = hal.alloc_elem_init("accum", self.cycles * self.N_ACCUM, INVALID)
 
     def accum(self, mix):
+        # segments with bigint cycles: the BigIntAccumState cells depend on the mix and are scattered now
+        # (witgen/mod.rs:186-207); every other segment has none
+        inj = self.pf.bigint_accum_injector(mix) if getattr(self.pf, "has_bigint", False) else None
+        if inj is not None:
+            self.hal.scatter(self.accum_buf, *inj)
         mix_buf = self.hal.copy_from_elem("mix", mix)
         self.circuit.step_accum(self.trace, self.data, self.accum_buf, self.global_, mix_buf)
         self.hal.eltwise_zeroize_elem(self.accum_buf)
@@ -528,8 +533,20 @@ class SegmentProver:
 
     def prove_core(self, pf):
         """SegmentProverImpl::prove_core (rv32im/src/prove/hal/mod.rs:143-224) from a PreflightResults, everything on
-        the device in one call (r0b200_prove_segment_rv32im). Returns (seal, roots, query positions, globals)."""
+        the device in one call (r0b200_prove_segment_rv32im). Returns (seal, roots, query positions, globals).
+        A segment with bigint cycles takes the protocol's own two-phase route instead (prove_begin -> mix -> host-built
+        BigIntAccum injector + step_accum on the device -> prove_finish), as include/r0b200.h prescribes for it."""
         hal = self.hal
+        if getattr(pf, "has_bigint", False):
+            wg = WitnessGenerator(hal, pf)
+            try:
+                glob = wg.global_.view().copy()
+                h, mix = self.begin(pf.po2, wg.code, wg.data, glob)
+                wg.accum(mix)
+                seal, roots, qpos = self.finish(h, wg.accum_buf)
+            finally:
+                wg.trace.close()
+            return seal, roots, qpos, glob
         st, keep = _trace_struct(pf)
         index, offsets, values = (_u32(a) for a in pf.injector)
         glob = _u32(pf.global_)

@@ -5,7 +5,7 @@ the executor runs the guest and cuts it into segments (execute/executor.rs), `Se
 and records, per cycle, what the circuit's step functions need (prove/witgen/preflight.rs): `RawPreflightCycle` (36 B)
 and `RawMemoryTransaction` (20 B) arrays (rv32im-sys/src/lib.rs:21-84), plus the injector CSR scatter and the global
 vector (witgen/mod.rs:226-380). That Rust cannot be built in this image (no cargo), so this module restates the part of
-it a guest without bigint needs:
+it a guest needs:
 
   execute/rv32im.rs      Emulator (RV32IM decode + step)                    -> Machine._exec
   execute/r0vm.rs        Risc0Machine (resume / suspend / ecalls / traps)   -> Machine
@@ -13,11 +13,14 @@ it a guest without bigint needs:
   execute/executor.rs    Executor::run (segment split, claims)              -> execute()
   execute/poseidon2.rs, prove/witgen/poseidon2.rs   paging permutation cycles, zcheck -> Poseidon2State / p2_* / Checksum
   execute/sha2.rs, prove/witgen/sha2.rs             SHA-256 compression cycles -> Sha2State / sha2_ecall
+  execute/bibc.rs, execute/bigint.rs, prove/witgen/bigint.rs, prove/witgen/byte_poly.rs
+                         bigint2 programs (nondet bytecode + verify program) -> BibcProgram, bigint_ecall(_preflight),
+                         BytePolyProgram, BigIntAccum (the mix-dependent accum injector, witgen/mod.rs:186-207)
   binfmt/src/image.rs    MemoryImage (sparse Poseidon2 Merkle image)        -> MemoryImage
   prove/witgen/preflight.rs, witgen/mod.rs          Preflight, injector, globals -> preflight(), PreflightResults
 
 Supported guest surface: RV32IM in machine or user mode, ecall terminate / read (fd supplied by a callback) / write /
-poseidon2 / sha2, user ecall + mret, fence. The bigint ecall raises NotImplementedError. It is plain Python: a po2 = 20
+poseidon2 / sha2 / bigint, user ecall + mret, fence. It is plain Python: a po2 = 20
 segment takes tens of seconds - it feeds tests and the benchmark's setup, not the timed region.
 """
 import gzip
@@ -59,6 +62,8 @@ POVW_NONCE_START_WADDR = 0x4400_0000
 POVW_NONCE_END_WADDR = 0x4400_0008
 REG_MAX = 32
 REG_A0, REG_A1, REG_A2, REG_A3, REG_A4, REG_A7 = 10, 11, 12, 13, 14, 17
+REG_SP, REG_T0, REG_T1, REG_T2, REG_T3 = 2, 5, 6, 7, 28
+USER_BIGINT_END_ADDR = 0xbfff_0000
 HOST_ECALL_TERMINATE, HOST_ECALL_READ, HOST_ECALL_WRITE, HOST_ECALL_POSEIDON2, HOST_ECALL_SHA2, HOST_ECALL_BIGINT = range(6)
 PFLAG_IS_ELEM, PFLAG_CHECK_OUT = 0x8000_0000, 0x4000_0000
 MAX_IO_BYTES, MAX_IO_WORDS = 1024, 4
@@ -788,7 +793,12 @@ class Machine:
             c.on_ecall_cycle(CS.MachineEcall, CS.ShaEcall, 0, 0, 0)
             sha2_ecall(c)
             return False
-        raise NotImplementedError("host ecall %d (bigint) is outside this restatement" % which)
+        if which == HOST_ECALL_BIGINT:        # r0vm.rs:573-585
+            c.pc = (c.pc + 4) & M32
+            c.on_ecall_cycle(CS.MachineEcall, CS.BigIntEcall, 0, 0, 0)
+            c.ecall_bigint()
+            return False
+        raise ValueError("unknown machine ecall %d" % which)
 
     def _ecall_read(self):
         c = self.c
@@ -997,6 +1007,305 @@ def sha2_ecall(c):
             c.store_u32(sha.state_out_addr + 7 - i, _bswap(sha.e))
     sha.round = 0
     step(CS.Decode)
+
+
+# ---- BigInt ecall (execute/bibc.rs, execute/bigint.rs, prove/witgen/bigint.rs, prove/witgen/byte_poly.rs) ------------
+BIGINT_WIDTH_WORDS, BIGINT_WIDTH_BYTES = 4, 16
+(BI_CONST, BI_LOAD, BI_STORE, BI_ADD, BI_SUB, BI_MUL, BI_REM, BI_QUO, BI_INV) = (0x2, 0x3, 0x4, 0x8, 0x9, 0xA, 0xB, 0xC, 0xE)
+POLY_RESET, POLY_SHIFT, POLY_SET_TERM, POLY_ADD_TOTAL, POLY_CARRY1, POLY_CARRY2, POLY_EQ_ZERO = range(7)
+MEM_READ, MEM_WRITE, MEM_CHECK = range(3)
+
+
+class BibcProgram:
+    """execute/bibc.rs:117-160: the 'nondet' half of a bigint blob - inputs, types, 64-bit constants, 64-bit ops"""
+
+    def __init__(self, data):
+        import struct
+        assert data[:4] == b"bibc" and struct.unpack_from("<I", data, 4)[0] == 1, "Invalid BigInt2 bytecode"
+        ni, nt, nc, no = struct.unpack_from("<4I", data, 8)
+        p = 24 + 16 * ni                                             # inputs are not needed to evaluate
+        self.types = [struct.unpack_from("<4Q", data, p + 32 * i)[0] for i in range(nt)]   # coeffs
+        p += 32 * nt
+        self.constants = list(struct.unpack_from("<%dQ" % nc, data, p))
+        p += 8 * nc
+        self.ops = []
+        for bits in struct.unpack_from("<%dQ" % no, data, p):
+            code = bits & 0xF
+            if code not in (BI_CONST, BI_LOAD, BI_STORE, BI_ADD, BI_SUB, BI_MUL, BI_REM, BI_QUO, BI_INV):
+                raise ValueError("Invalid BigInt2 bytecode")
+            self.ops.append((code, (bits >> 4) & 0xFFF, (bits >> 16) & 0xFFFFFF, (bits >> 40) & 0xFFFFFF))
+
+    def eval(self, io):
+        """bibc.rs:162-221 over Python integers (`/` and `%` of malachite's Integer truncate towards zero)"""
+        regs = [0] * len(self.ops)
+        for i, (code, rt, a, b) in enumerate(self.ops):
+            if code == BI_CONST:
+                regs[i] = sum(self.constants[a + k] << (64 * k) for k in range(b))
+            elif code == BI_LOAD:
+                regs[i] = io.load(a >> 16, a & 0xFFFF, -(-self.types[rt] // 16) * 16)
+            elif code == BI_STORE:
+                io.store(a >> 16, a & 0xFFFF, -(-self.types[rt] // 16) * 16, abs(regs[b]))
+            else:
+                assert a < i and b < i
+                x, y = regs[a], regs[b]
+                if code == BI_ADD:
+                    regs[i] = x + y
+                elif code == BI_SUB:
+                    regs[i] = x - y
+                elif code == BI_MUL:
+                    regs[i] = x * y
+                elif code == BI_REM:
+                    regs[i] = abs(x) % abs(y) * (-1 if x < 0 else 1)
+                elif code == BI_QUO:
+                    regs[i] = abs(x) // abs(y) * (-1 if (x < 0) != (y < 0) else 1)
+                else:
+                    regs[i] = pow(abs(x) % abs(y), -1, abs(y))     # raises ValueError when not invertible
+
+
+def _aligned_waddr(addr):
+    if addr % 4:
+        raise ValueError("%#010x is an unaligned address" % addr)
+    return addr // 4
+
+
+def _check_bigint_addr(waddr, mode):
+    if not ((waddr >= ZERO_PAGE_END_ADDR // 4 and mode == 1) or waddr < USER_BIGINT_END_ADDR // 4):
+        raise ValueError("Invalid bigint address")
+
+
+class _BigIntIO:
+    """execute/bigint.rs:37-133: loads read guest memory (no transactions), stores only fill the witness map"""
+
+    def __init__(self, c, mode):
+        self.c, self.mode, self.witness = c, mode, {}
+
+    def _base(self, arena):
+        return _aligned_waddr(self.c.load_u32(LOAD, MACHINE_REGS_ADDR // 4 + arena))
+
+    def load(self, arena, offset, count):
+        start = self._base(arena) + offset * BIGINT_WIDTH_WORDS
+        _check_bigint_addr(start, self.mode)
+        words = -(-count // 4)
+        limbs = [self.c.load_u32(LOAD, start + i) for i in range(words)]
+        if limbs and count % 4:
+            limbs[-1] &= (1 << (8 * (count % 4))) - 1
+        return sum(w << (32 * i) for i, w in enumerate(limbs))
+
+    def store(self, arena, offset, count, value):
+        addr = self._base(arena) + offset * BIGINT_WIDTH_WORDS
+        _check_bigint_addr(addr, self.mode)
+        nlimbs = (value.bit_length() + 31) // 32
+        if count < nlimbs * 4:
+            raise ValueError("bigint_store: count (%d bytes) too small for value (%d bytes)" % (count, nlimbs * 4))
+        if count % BIGINT_WIDTH_BYTES:
+            raise ValueError("bigint_store: count (%d) is not a multiple of %d" % (count, BIGINT_WIDTH_BYTES))
+        raw = value.to_bytes(nlimbs * 4, "little")
+        filled = 0
+        for ci in range(0, len(raw), BIGINT_WIDTH_BYTES):
+            chunk = raw[ci:ci + BIGINT_WIDTH_BYTES]
+            self.witness[addr + (ci // BIGINT_WIDTH_BYTES) * BIGINT_WIDTH_WORDS] = chunk + b"\x00" * (BIGINT_WIDTH_BYTES - len(chunk))
+            filled += 1
+        for i in range(count // BIGINT_WIDTH_BYTES - filled):
+            self.witness[addr + (filled + i) * BIGINT_WIDTH_WORDS] = b"\x00" * BIGINT_WIDTH_BYTES
+
+
+def bigint_ecall(c):
+    """execute/bigint.rs:172-226 -> (mode, verify_program_ptr (word address of the word BEFORE the program),
+    verify_program_size, witness {word address: 16 bytes}). Only the loads of t0 and t2 are recorded transactions."""
+    m = MACHINE_REGS_ADDR // 4
+    mode = c.load_u32(RECORD, m + REG_T0)
+    if mode not in (0, 1):
+        raise ValueError("Invalid mode for bigint ecall: %d" % mode)
+    blob_ptr = _aligned_waddr(c.load_u32(LOAD, m + REG_A0))
+    nondet_ptr = _aligned_waddr(c.load_u32(LOAD, m + REG_T1))
+    verify_ptr = _aligned_waddr(c.load_u32(RECORD, m + REG_T2)) - 1
+    consts_ptr = _aligned_waddr(c.load_u32(LOAD, m + REG_T3))
+    nondet_size = c.load_u32(LOAD, blob_ptr)
+    verify_size = c.load_u32(LOAD, blob_ptr + 1)
+    consts_size = c.load_u32(LOAD, blob_ptr + 2)
+    data = b"".join(c.load_u32(LOAD, nondet_ptr + i).to_bytes(4, "little") for i in range(nondet_size))
+    io = _BigIntIO(c, mode)
+    BibcProgram(data).eval(io)
+    for i in range(verify_size):
+        c.load_u32(LOAD, verify_ptr + 1 + i)
+    for i in range(consts_size):
+        c.load_u32(LOAD, consts_ptr + i)
+    return mode, verify_ptr, verify_size, io.witness
+
+
+# polynomials with small integer coefficients, lowest degree first; lengths follow the reference's 4-lane chunks
+# (byte_poly.rs:128-262) because the carry pass walks `len()` coefficients and `get` is bounds-checked
+def _bp_add(a, b):
+    n = max(len(a), len(b))
+    return [(a[i] if i < len(a) else 0) + (b[i] if i < len(b) else 0) for i in range(n)]
+
+
+def _bp_mul(a, b):
+    r = [0] * (len(a) + len(b))
+    for i, x in enumerate(a):
+        if x:
+            for j, y in enumerate(b):
+                r[i + j] += x * y
+    return r
+
+
+class BytePolyProgram:
+    """byte_poly.rs:33-126: what the verify program computes, over the integers"""
+
+    def __init__(self):
+        self.in_carry = False
+        self.total_carry = []
+        self.reset()
+
+    def reset(self):
+        self.poly, self.term, self.total = [0] * 4, [1, 0, 0, 0], [0] * 4
+
+    def step(self, poly_op, coeff, witness):
+        delta = list(witness)
+        new_poly = _bp_add(self.poly, delta)
+        if poly_op == POLY_RESET:
+            self.reset()
+        elif poly_op == POLY_SHIFT:
+            self.poly = [0] * BIGINT_WIDTH_BYTES + new_poly
+        elif poly_op == POLY_SET_TERM:
+            self.poly, self.term = [0] * 4, new_poly
+        elif poly_op == POLY_ADD_TOTAL:
+            self.total = _bp_add(self.total, [x * coeff for x in _bp_mul(new_poly, self.term)])
+            self.term, self.poly = [1, 0, 0, 0], [0] * 4
+        elif poly_op == POLY_CARRY1:
+            self.poly = _bp_add(self.poly, [(x - 128) * 64 * 256 for x in delta])
+        elif poly_op == POLY_CARRY2:
+            self.poly = _bp_add(self.poly, [x * 256 for x in delta])
+        elif poly_op == POLY_EQ_ZERO:
+            self.total = _bp_add(self.total, _bp_mul([-256, 1, 0, 0], new_poly))
+            if any(self.total):
+                raise ValueError("Invalid eqz in bigint program")
+            self.reset()
+            self.in_carry = False
+        else:
+            raise ValueError("Invalid poly_op in bigint program")
+
+
+class BigIntState:
+    """prove/witgen/bigint.rs:36-45: the 22 injected cells of a bigint cycle"""
+
+    def __init__(self, is_ecall, mode, pc, poly_op, coeff, bytes_, next_state):
+        self.is_ecall, self.mode, self.pc, self.poly_op, self.coeff = is_ecall, mode, pc, poly_op, coeff
+        self.bytes, self.next_state = bytes(bytes_), next_state
+
+    def clone(self):
+        return BigIntState(self.is_ecall, self.mode, self.pc, self.poly_op, self.coeff, self.bytes, self.next_state)
+
+    def as_array(self):
+        return [int(self.is_ecall), self.mode, self.pc, self.poly_op, self.coeff] + list(self.bytes) + [self.next_state]
+
+
+def bigint_ecall_preflight(c):
+    """prove/witgen/bigint.rs:104-190,248-268: one BigIntEcall cycle, then one BigIntStep cycle per word of the verify
+    program - each reads / writes / checks one 16-byte chunk and advances the byte polynomials"""
+    mode, verify_ptr, _size, witness = bigint_ecall(c)
+    st = BigIntState(True, mode, verify_ptr, POLY_RESET, 0, bytes(16), CS.BigIntStep)
+    prog = BytePolyProgram()
+    c.on_bigint_cycle(CS.BigIntEcall, st)
+    m = MACHINE_REGS_ADDR // 4
+    while st.next_state == CS.BigIntStep:
+        st.pc += 1
+        insn = c.load_u32(RECORD, st.pc)
+        mem_op, poly_op = (insn >> 28) & 0xF, (insn >> 24) & 0xF
+        if mem_op > MEM_CHECK:
+            raise ValueError("Invalid mem_op in bigint program")
+        if poly_op > POLY_EQ_ZERO:
+            raise ValueError("Invalid poly_op in bigint program")
+        coeff, reg, offset = ((insn >> 21) & 7) - 4, (insn >> 16) & 0x1F, insn & 0xFFFF
+        addr = _aligned_waddr(c.load_u32(RECORD, m + reg)) + offset * BIGINT_WIDTH_WORDS
+        if mem_op == MEM_CHECK and poly_op != POLY_RESET:
+            if not prog.in_carry:
+                prog.in_carry = True
+                tc, carry = list(prog.total), 0
+                for i in range(len(tc)):
+                    v = tc[i] + carry
+                    if v % 256:
+                        raise ValueError("bad carry")
+                    tc[i] = carry = v // 256
+                prog.total_carry = tc
+            out = bytearray(16)
+            for i in range(16):
+                value = (prog.total_carry[offset * BIGINT_WIDTH_BYTES + i] + 128 * 256 * 64) & M32
+                if poly_op == POLY_CARRY1:
+                    out[i] = (value >> 14) & 0xFF
+                elif poly_op == POLY_CARRY2:
+                    out[i] = (value >> 8) & 0x3F
+                elif poly_op in (POLY_SHIFT, POLY_EQ_ZERO):
+                    out[i] = value & 0xFF
+                else:
+                    raise ValueError("Invalid poly_op in bigint program")
+            st.bytes = bytes(out)
+        elif mem_op == MEM_READ:
+            st.bytes = b"".join(c.load_u32(RECORD, addr + i).to_bytes(4, "little") for i in range(BIGINT_WIDTH_WORDS))
+        elif addr != 0:
+            if addr not in witness:
+                raise ValueError("Missing bigint witness: %#x" % (addr * 4))
+            st.bytes = witness[addr]
+            if mem_op == MEM_WRITE:
+                for i in range(BIGINT_WIDTH_WORDS):
+                    c.store_u32(addr + i, int.from_bytes(st.bytes[4 * i:4 * i + 4], "little"))
+        prog.step(poly_op, coeff, st.bytes)
+        st.is_ecall = False
+        st.poly_op, st.coeff = poly_op, coeff + 4
+        st.next_state = CS.Decode if poly_op == POLY_RESET else CS.BigIntStep
+        c.on_bigint_cycle(CS.BigIntStep, st)
+
+
+def ext_sub(a, b):
+    return tuple((x - y) % P for x, y in zip(a, b))
+
+
+class BigIntAccum:
+    """byte_poly.rs:403-475: the same program evaluated at the accum mix point (an extension element) - the values of the
+    BigIntAccumState registers, which depend on the transcript's mix and are therefore injected in the accum phase
+    (witgen/mod.rs:186-207)"""
+
+    def __init__(self, mix):
+        self.powers, cur = [], (1, 0, 0, 0)
+        for _ in range(BIGINT_WIDTH_BYTES + 1):
+            self.powers.append(cur)
+            cur = ext_mul(cur, mix)
+        self.neg_poly = (0, 0, 0, 0)
+        for pw in self.powers[:BIGINT_WIDTH_BYTES]:
+            self.neg_poly = ext_add(self.neg_poly, ext_mul(pw, (128, 0, 0, 0)))
+        self.reset()
+
+    def reset(self):
+        self.poly, self.term, self.total = (0, 0, 0, 0), (1, 0, 0, 0), (0, 0, 0, 0)
+
+    def step(self, st):
+        delta = (0, 0, 0, 0)
+        for b, pw in zip(st.bytes, self.powers):
+            delta = ext_add(delta, ext_mul(pw, (b, 0, 0, 0)))
+        new_poly = ext_add(self.poly, delta)
+        op = st.poly_op
+        if op == POLY_RESET:
+            self.reset()
+        elif op == POLY_SHIFT:
+            self.poly = ext_mul(new_poly, self.powers[BIGINT_WIDTH_BYTES])
+        elif op == POLY_SET_TERM:
+            self.poly, self.term = (0, 0, 0, 0), new_poly
+        elif op == POLY_ADD_TOTAL:
+            coeff = ((st.coeff - 4) % P, 0, 0, 0)
+            self.total = ext_add(self.total, ext_mul(ext_mul(coeff, self.term), new_poly))
+            self.poly, self.term = (0, 0, 0, 0), (1, 0, 0, 0)
+        elif op == POLY_CARRY1:
+            self.poly = ext_add(self.poly, ext_mul(ext_sub(delta, self.neg_poly), (64 * 256, 0, 0, 0)))
+        elif op == POLY_CARRY2:
+            self.poly = ext_add(self.poly, ext_mul(delta, (256, 0, 0, 0)))
+        elif op == POLY_EQ_ZERO:
+            goal = ext_add(self.total, ext_mul(new_poly, ext_sub(self.powers[1], (256, 0, 0, 0))))
+            if any(goal):
+                raise ValueError("Invalid eqz in bigint accum")
+            self.reset()
+
+    def as_array(self):
+        return list(self.poly) + list(self.term) + list(self.total)
 
 
 # ---- Poseidon2 cycles (execute/poseidon2.rs:37-148, prove/witgen/poseidon2.rs) --------------------------------------
@@ -1227,6 +1536,14 @@ class _ExecCtx:
     def on_sha2_cycle(self, cur, sha2):
         self.user_cycles += 1
 
+    def ecall_bigint(self):
+        # executor.rs:652-656, execute/bigint.rs:150-170: run the nondet program, put its results into guest memory
+        _mode, _ptr, verify_size, witness = bigint_ecall(self)
+        for addr in sorted(witness):
+            for i in range(BIGINT_WIDTH_WORDS):
+                self.store_u32(addr + i, int.from_bytes(witness[addr][4 * i:4 * i + 4], "little"))
+        self.user_cycles += verify_size + 1
+
     def on_terminate(self, a0, a1):
         self.terminate_state = (a0, a1)
         self.output_digest = tuple(self.load_u32(PEEK, GLOBAL_OUTPUT_ADDR // 4 + i) for i in range(8))
@@ -1310,8 +1627,10 @@ class _Preflight:
         self.segment = segment
         self.rand_z = tuple(int(x) for x in rand_z)
         self.cycles = []     # [state, pc, major, minor, machine_mode, user_cycle, txn_idx, paging_idx, bigint_idx, d0, d1]
-        self.backs = []      # None | ("ecall", s0, s1, s2) | ("p2", Poseidon2State) | ("sha2", Sha2State)
+        self.backs = []      # None | ("ecall", s0, s1, s2) | ("p2", Poseidon2State) | ("sha2", Sha2State) | ("bigint", BigIntState)
         self.txns = []       # [addr, cycle, word, prev_cycle, prev_word]
+        self.bigint_bytes = bytearray()   # 16 bytes per bigint cycle (preflight.rs:402-404), indexed by the cycle's bigint_idx
+        self.bigint_idx = 0
         self.pager = PagedMemory(segment.partial_image)
         self.pc = 0
         self.machine_mode = 0
@@ -1329,9 +1648,11 @@ class _Preflight:
 
     # -- cycles
     def add_cycle(self, state, pc, major, minor, paging_idx, back):
-        self.cycles.append([state, pc, major, minor, self.machine_mode, self.user_cycle, self.txn_idx, paging_idx, 0, 0, 0])
+        self.cycles.append([state, pc, major, minor, self.machine_mode, self.user_cycle, self.txn_idx, paging_idx, self.bigint_idx,
+                            0, 0])
         self.backs.append(back)
         self.txn_idx = len(self.txns)
+        self.bigint_idx = len(self.bigint_bytes)
 
     def add_cycle_special(self, cur_state, next_state, pc, paging_idx, back):
         self.add_cycle(next_state, pc, 7 + cur_state // 8, cur_state % 8, paging_idx, back)
@@ -1357,6 +1678,14 @@ class _Preflight:
 
     def on_poseidon2_cycle(self, cur_state, p2):
         self.add_cycle_special(cur_state, p2.next_state, self.pc, node_addr_to_idx(p2.buf_out_addr), ("p2", p2.clone()))
+        self.user_cycles += 1
+
+    def ecall_bigint(self):                        # preflight.rs:699-701
+        bigint_ecall_preflight(self)
+
+    def on_bigint_cycle(self, cur_state, st):      # preflight.rs:471-481
+        self.bigint_bytes += st.bytes
+        self.add_cycle_special(cur_state, st.next_state, self.pc, 0, ("bigint", st.clone()))
         self.user_cycles += 1
 
     def on_sha2_cycle(self, cur_state, sha2):      # preflight.rs:677-686
@@ -1623,8 +1952,9 @@ class PreflightResults:
         for i, f in enumerate(("addr", "cycle", "word", "prev_cycle", "prev_word")):
             tx[f] = tarr[:, i]
         self.txns = tx
-        self.bigint_bytes = np.zeros(0, dtype=np.uint8)
+        self.bigint_bytes = np.frombuffer(bytes(pf.bigint_bytes), dtype=np.uint8).copy()
         self.backs = pf.backs
+        self.has_bigint = any(b is not None and b[0] == "bigint" for b in pf.backs)
         self.user_cycles = segment.suspend_cycle
         self.injector = self._build_injector(pf)
         self.global_ = self._build_global()
@@ -1643,6 +1973,9 @@ class PreflightResults:
         sha_fp = [layout_col(T, sst + nm + "._super") for nm in ("stateInAddr", "stateOutAddr", "dataAddr", "count", "kAddr", "round",
                                                                   "nextState")]
         sha_bits = [layout_col(T, sst + "%s[0]._super" % nm) for nm in ("a", "e", "w")]
+        bst = "instResult.arm12.state."
+        big_cols = [layout_col(T, bst + nm + "._super") for nm in ("isEcall", "mode", "pc", "polyOp", "coeff")]
+        big_cols += [layout_col(T, bst + "bytes[%d]._super" % i) for i in range(16)] + [layout_col(T, bst + "nextState._super")]
         cycle_col = layout_col(T, "cycle._super")
         pc_low, pc_high = layout_col(T, "nextPcLow._super"), layout_col(T, "nextPcHigh._super")
         next_state, next_mm = layout_col(T, "nextState_0._super"), layout_col(T, "nextMachineMode._super")
@@ -1652,6 +1985,9 @@ class PreflightResults:
             if back is not None:
                 if back[0] == "ecall":
                     for col, v in zip(ecall, back[1:4]):
+                        inj.set(row, col, v)
+                elif back[0] == "bigint":         # witgen/mod.rs:261-265
+                    for col, v in zip(big_cols, back[1].as_array()):
                         inj.set(row, col, v)
                 elif back[0] == "sha2":           # witgen/mod.rs:253-260: 7 field columns, then a / e / w bit by bit
                     for col, v in zip(sha_fp, back[1].fp_array()):
@@ -1668,6 +2004,25 @@ class PreflightResults:
             inj.set(row, next_state, cyc[0])
             inj.set(row, next_mm, cyc[4])
             inj.push()
+        return inj.arrays()
+
+    def bigint_accum_injector(self, mix):
+        """witgen/mod.rs:186-207: the BigIntAccumState cells of every bigint cycle for the transcript's accum mix (36
+        Montgomery words; the last four are the evaluation point) -> CSR scatter arrays for the ACCUM matrix, or None
+        when the segment has no bigint cycles"""
+        if not self.has_bigint:
+            return None
+        rinv = pow(1 << 32, -1, P)
+        point = tuple(int(w) * rinv % P for w in np.asarray(mix, dtype=np.uint64)[-4:])
+        A = "kLayout_TopAccum"
+        cols = [layout_col(A, "user._0.state.%s._super" % nm) + i for nm in ("poly", "term", "total") for i in range(4)]
+        acc, inj = BigIntAccum(point), Injector(self.rows)
+        for row, back in enumerate(self.backs):
+            if back is not None and back[0] == "bigint":
+                acc.step(back[1])
+                for col, v in zip(cols, acc.as_array()):
+                    inj.set(row, col, v)
+                inj.push()
         return inj.arrays()
 
     def _build_global(self):
@@ -1879,6 +2234,49 @@ def sha2_guest(message=b"abc", loops=3):
     asm.li(t3, SHA2_GUEST_OUT_ADDR)
     asm.load(2, a4, t3, 0)               # lw: the stored state is read back by an ordinary instruction
     asm.load(2, a5, t3, 28)
+    asm.host_terminate(0, 0)
+    entry, image = asm.program()
+    return MemoryImage.new_kernel(entry, image)
+
+
+BIGINT_GUEST_OUT_ADDR = 0x00501060
+
+
+def bigint_modmul_guest(blob, a, b, n, loops=3):
+    """machine-mode guest that runs a bigint2 `modmul_256` blob (header: nondet / verify / consts / temp sizes in words,
+    then the bibc program, the verify program and the constants; zkvm/platform/src/syscall.rs:1044-1115 shows how a guest
+    lays the registers out): a, b, n are 256-bit operands at a1, a2, a3, the product a * b mod n lands at a4
+    (BIGINT_GUEST_OUT_ADDR), the quotient in the scratch space sp points at."""
+    import struct
+    nondet_size, verify_size, consts_size, temp_size = struct.unpack_from("<4I", blob, 0)
+    assert len(blob) == 16 + 4 * (nondet_size + verify_size + consts_size)
+    blob_addr, a_addr, temp_addr = 0x00500000, 0x00501000, 0x00501100
+    asm = Assembler()
+    for i in range(len(blob) // 4):
+        asm.word(blob_addr + 4 * i, int.from_bytes(blob[4 * i:4 * i + 4], "little"))
+    for k, v in enumerate((a, b, n)):
+        for i in range(8):
+            asm.word(a_addr + 32 * k + 4 * i, (v >> (32 * i)) & M32)
+    a4, a5, t4 = 14, 15, 29
+    asm.addi(a4, 0, 0)
+    asm.li(a5, loops)
+    asm.addi(a4, a4, 1)
+    asm.blt(a4, a5, -4)
+    asm.li(REG_T0, 0)                                   # mode
+    asm.li(REG_A0, blob_addr)
+    asm.li(REG_T1, blob_addr + 16)
+    asm.li(REG_T2, blob_addr + 16 + 4 * nondet_size)
+    asm.li(REG_T3, blob_addr + 16 + 4 * (nondet_size + verify_size))
+    asm.li(REG_A1, a_addr)
+    asm.li(REG_A2, a_addr + 32)
+    asm.li(REG_A3, a_addr + 64)
+    asm.li(REG_A4, BIGINT_GUEST_OUT_ADDR)
+    asm.li(REG_SP, temp_addr)
+    asm.li(REG_A7, HOST_ECALL_BIGINT)
+    asm.ecall()
+    asm.li(t4, BIGINT_GUEST_OUT_ADDR)
+    asm.load(2, a5, t4, 0)
+    asm.load(2, a5, t4, 28)
     asm.host_terminate(0, 0)
     entry, image = asm.program()
     return MemoryImage.new_kernel(entry, image)

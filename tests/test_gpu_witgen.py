@@ -9,7 +9,7 @@ import oracle_lib as O
 import witgen_ref as W
 from risc0_b200 import B200Hal, SegmentProver, WitnessGenerator
 from risc0_b200 import preflight as PF
-from test_preflight import all_insn_guest
+from test_preflight import all_insn_guest, bigint_guest
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (W.have_ref() and O.have_ref()), reason="oracle/_ref not built")]
 
@@ -26,6 +26,7 @@ def segments():
            "all_insn": PF.execute(all_insn_guest(), segment_po2=14)[0]}
     out["user_mode"] = PF.execute(PF.user_mode_guest(30), segment_po2=14)[0]
     out["sha2"] = PF.execute(PF.sha2_guest(bytes(range(200))), segment_po2=14)[0]   # 4 blocks through the sha2 ecall
+    out["bigint"] = PF.execute(bigint_guest(2)[0], segment_po2=14)[0]               # modmul_256 through the bigint ecall
     split = PF.execute(PF.simple_loop_kernel(4000), segment_po2=13)
     out["split_first"], out["split_second"] = split[0], split[1]
     return out
@@ -41,7 +42,7 @@ def seg(name):
     return SEGS[name]
 
 
-@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second", "user_mode", "sha2"])
+@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second", "user_mode", "sha2", "bigint"])
 def test_device_witgen_and_accum_match_reference(hal, name):
     pf = PF.PreflightResults(seg(name), (11, 12, 13, 14))
     want_glob, want_data = W.ref_generate_witness(pf)
@@ -68,7 +69,7 @@ def test_device_witgen_reports_bad_traces(hal):
     WitnessGenerator(hal, pf)                        # the context is still usable afterwards
 
 
-@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "user_mode", "sha2"])
+@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "user_mode", "sha2", "bigint"])
 def test_prove_core_from_trace_bit_exact_and_valid(hal, name):
     pf = PF.PreflightResults(seg(name), (21, 22, 23, 24))
     po2 = pf.po2
@@ -100,6 +101,18 @@ def test_two_phase_with_device_accum(hal):
     seal, roots, _ = prover.finish(h, wg.accum_buf)
     want = SegmentProver(hal).prove_core(pf)[0]
     assert np.array_equal(seal, want)
+
+
+def test_one_call_segment_path_refuses_bigint_segments(hal):
+    # r0b200_prove_segment cannot know the mix-dependent BigIntAccum cells (include/r0b200.h): step_accum finds them unset
+    # and the call fails loudly instead of producing a seal; the two-phase route (SegmentProver.prove_core picks it) works
+    pf = PF.PreflightResults(seg("bigint"), (51, 52, 53, 54))
+    prover = SegmentProver(hal)
+    with pytest.raises(Exception) as ei:
+        prover.prove_segment(prover.upload_segment(pf))
+    assert "unset" in str(ei.value).lower() or "accum" in str(ei.value).lower()
+    seal = prover.prove_core(pf)[0]                    # the context is still usable, and the right route gives a valid seal
+    assert O.verify_with_validity(seal)[1]
 
 
 def test_verifier_rejects_a_witness_that_violates_constraints(hal):

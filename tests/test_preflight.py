@@ -164,6 +164,51 @@ def test_sha2_ecall_guest(message):
     assert digest == hashlib.sha256(message).digest()
 
 
+def bigint_guest(seed=0):
+    """modmul_256 from the reference's bigint2 crate (tests/golden/bigint_modmul_256.blob = risc0/bigint2/src/field/
+    modmul_256.blob, a reference-held fixture) on the secp256k1 prime"""
+    import os
+    blob = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bigint_modmul_256.blob"), "rb").read()
+    rng = np.random.default_rng(100 + seed)
+    n = 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffefffffc2f
+    a, b = (int.from_bytes(rng.bytes(32), "little") % n for _ in range(2))
+    return PF.bigint_modmul_guest(blob, a, b, n), (a, b, n)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_bigint_ecall_guest(seed):
+    """the bigint ecall (execute/bigint.rs + bibc.rs, prove/witgen/bigint.rs + byte_poly.rs): the product the guest leaves
+    in memory is a * b mod n; the reference's compiled witness generator accepts the trace (BigIntEcall / BigIntStep
+    cycles, the 16 witness bytes per cycle) and the generated step functions reproduce it; with the BigIntAccumState cells
+    computed from the mix (witgen/mod.rs:186-207) the reference accum runs and EVERY constraint holds - including the
+    bigint accumulator's own polynomial identity at the mix point."""
+    image, (a, b, n) = bigint_guest(seed)
+    segs = PF.execute(image, segment_po2=14)
+    assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
+    pf, _, _, _ = check_segment(segs[0], seed=6)
+    assert pf.has_bigint and len(pf.bigint_bytes) == 16 * 33        # ecall cycle + 32 verify-program words
+    kinds = list(zip(pf.cycles["major"].tolist(), pf.cycles["minor"].tolist()))
+    assert kinds.count((12, 0)) == 1 and kinds.count((12, 1)) == 32
+    out = {}
+    for t in pf.txns:
+        addr = int(t["addr"]) * 4
+        if PF.BIGINT_GUEST_OUT_ADDR <= addr < PF.BIGINT_GUEST_OUT_ADDR + 32 and int(t["cycle"]) % 2 == 1:
+            out[addr] = int(t["word"])
+    assert sum(out[PF.BIGINT_GUEST_OUT_ADDR + 4 * i] << (32 * i) for i in range(8)) == a * b % n
+    # BigIntAccum cells computed from another mix are caught: the step recomputes the cells it was given and finds them
+    # inconsistent (the generated code reports it; the reference's C++ throws the same failure from inside its thread
+    # pool, which would take the process down)
+    glob, data = W.ref_generate_witness(pf)
+    mix, _ = mixes(6)
+    other = mix.copy()
+    other[-1] ^= 1
+    accum = np.full(W.N_ACCUM * pf.rows, W.INVALID, dtype=np.uint32)
+    W.scatter(accum, *pf.bigint_accum_injector(other))
+    with pytest.raises(RuntimeError) as ei:
+        W.host_accum(pf, glob, data, mix, accum=accum)
+    assert "Inconsistent set" in str(ei.value) or "eqz" in str(ei.value)
+
+
 def test_user_mode_guest_with_kernel_traps():
     # user-mode code under a machine-mode kernel: mret into user mode, user ecall -> kernel dispatch -> terminate
     segs = PF.execute(PF.user_mode_guest(30), segment_po2=14)

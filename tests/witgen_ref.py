@@ -61,6 +61,19 @@ def _trace(pf, cycles, txns, bigint):
                              pf.table_split_cycle)
 
 
+def _bigint_bytes(pf):
+    b = np.ascontiguousarray(pf.bigint_bytes, dtype=np.uint8)
+    return b.copy() if len(b) else np.zeros(1, dtype=np.uint8)
+
+
+def _inject_bigint_accum(pf, accum, mix):
+    """witgen/mod.rs:186-207: segments with bigint cycles get their BigIntAccumState cells (a function of the mix)
+    scattered into accum before step_accum"""
+    inj = pf.bigint_accum_injector(mix) if getattr(pf, "has_bigint", False) else None
+    if inj is not None:
+        scatter(accum, *inj)
+
+
 def scatter(into, index, offsets, values):
     into[offsets] = values    # Hal::scatter (cpu.rs:598-615); offsets are unique per (row, col)
     return into
@@ -77,7 +90,7 @@ def ref_generate_witness(pf):
     data = np.full(N_DATA * rows, INVALID, dtype=np.uint32)
     scatter(data, *pf.injector)
     glob = pf.global_.copy()
-    cycles, txns, bigint = pf.cycles.copy(), pf.txns.copy(), np.zeros(max(len(pf.bigint_bytes), 1), dtype=np.uint8)
+    cycles, txns, bigint = pf.cycles.copy(), pf.txns.copy(), _bigint_bytes(pf)
     bufs = RawExecBuffers(_buf(glob, 1, N_GLOBAL), _buf(data, rows, N_DATA))
     tr = _trace(pf, cycles, txns, bigint)
     err = ref_lib().risc0_circuit_rv32im_cpu_witgen(C.c_uint32(0), C.byref(bufs), C.byref(tr), C.c_uint32(rows))
@@ -88,10 +101,16 @@ def ref_generate_witness(pf):
 
 def ref_accum(pf, glob, data, mix):
     """WitnessGenerator::accum (witgen/mod.rs:178-224) with the reference C++ step_TopAccum + prefix sums"""
+    accum = np.full(N_ACCUM * pf.rows, INVALID, dtype=np.uint32)
+    _inject_bigint_accum(pf, accum, np.ascontiguousarray(mix, dtype=np.uint32))
+    return ref_accum_prefilled(pf, glob, data, mix, accum)
+
+
+def ref_accum_prefilled(pf, glob, data, mix, accum):
+    """the reference step_accum on an accum matrix the caller has INVALID-filled and injected"""
     rows = pf.rows
-    accum = np.full(N_ACCUM * rows, INVALID, dtype=np.uint32)
     data, glob, mix = data.copy(), glob.copy(), np.ascontiguousarray(mix, dtype=np.uint32).copy()
-    cycles, txns, bigint = pf.cycles.copy(), pf.txns.copy(), np.zeros(max(len(pf.bigint_bytes), 1), dtype=np.uint8)
+    cycles, txns, bigint = pf.cycles.copy(), pf.txns.copy(), _bigint_bytes(pf)
     bufs = RawAccumBuffers(_buf(data, rows, N_DATA), _buf(accum, rows, N_ACCUM), _buf(glob, 1, N_GLOBAL), _buf(mix, 1, N_MIX))
     tr = _trace(pf, cycles, txns, bigint)
     err = ref_lib().risc0_circuit_rv32im_cpu_accum(C.byref(bufs), C.byref(tr), C.c_uint32(rows))
@@ -138,7 +157,7 @@ def host_generate_witness(pf):
     data = np.full(N_DATA * rows, INVALID, dtype=np.uint32)
     scatter(data, *pf.injector)
     glob = pf.global_.copy()
-    bigint = np.zeros(max(len(pf.bigint_bytes), 1), dtype=np.uint8)
+    bigint = _bigint_bytes(pf)
     err = np.zeros(4, dtype=np.uint32)
     host_lib().wg_host_witgen(C.c_void_p(pf.cycles.ctypes.data), C.c_uint32(rows), C.c_void_p(pf.txns.ctypes.data),
                               C.c_uint32(len(pf.txns)), C.c_void_p(bigint.ctypes.data), C.c_uint32(len(pf.bigint_bytes)),
@@ -148,11 +167,14 @@ def host_generate_witness(pf):
     return zeroize(glob), zeroize(data)
 
 
-def host_accum(pf, glob, data, mix):
+def host_accum(pf, glob, data, mix, accum=None):
+    """generated step_TopAccum (host build); `accum`: a matrix the caller has INVALID-filled and injected itself"""
     rows = pf.rows
-    accum = np.full(N_ACCUM * rows, INVALID, dtype=np.uint32)
     data, glob, mix = data.copy(), glob.copy(), np.ascontiguousarray(mix, dtype=np.uint32).copy()
-    bigint = np.zeros(max(len(pf.bigint_bytes), 1), dtype=np.uint8)
+    if accum is None:
+        accum = np.full(N_ACCUM * rows, INVALID, dtype=np.uint32)
+        _inject_bigint_accum(pf, accum, mix)
+    bigint = _bigint_bytes(pf)
     err = np.zeros(4, dtype=np.uint32)
     host_lib().wg_host_accum(C.c_void_p(pf.cycles.ctypes.data), C.c_uint32(rows), C.c_void_p(pf.txns.ctypes.data),
                              C.c_uint32(len(pf.txns)), C.c_void_p(bigint.ctypes.data), C.c_uint32(len(pf.bigint_bytes)),
