@@ -229,8 +229,11 @@ r0b200_err r0b200_accum_rv32im(r0b200_ctx* ctx, r0b200_trace* trace, uint32_t* d
  *   r0b200_prove_segment  : proves an uploaded segment (it can be proved again; free it with r0b200_segment_free).
  *                           global_out_host (90 words, may be NULL) receives the globals after witness generation.
  *   r0b200_prove_segment_rv32im : upload + prove + free in one call.
- * Segments with bigint cycles need the BigIntAccum injector, which depends on the mix (witgen/mod.rs:186-207): they go
- * through r0b200_prove_begin / r0b200_accum_rv32im / r0b200_prove_finish instead. */
+ * Segments with bigint cycles: the BigIntAccumState cells of those rows depend on the mix (witgen/mod.rs:186-207,
+ * byte_poly.rs:403-475). r0b200_segment_upload reads what they need out of the trace while it is still on the host
+ * (the 16 witness bytes and the verify-program word of each bigint cycle), and r0b200_prove_segment evaluates them at
+ * the drawn mix and scatters them into accum before step_accum - nothing extra to pass. A caller that owns witness
+ * generation itself (r0b200_prove_begin / r0b200_accum_rv32im / r0b200_prove_finish) scatters them as the reference does. */
 typedef struct r0b200_segment r0b200_segment;
 r0b200_err r0b200_segment_upload(r0b200_ctx* ctx, uint32_t po2, const r0b200_preflight_trace* trace_host,
                                  const uint32_t* global_host, const uint32_t* inj_index_host, size_t inj_index_len,

@@ -694,8 +694,112 @@ struct r0b200_segment {
   uint32_t *d_index = nullptr, *d_offsets = nullptr, *d_values = nullptr;
   size_t index_len = 0, nvals = 0;
   std::vector<uint32_t> global;
+  // bigint cycles of the trace (major 12), extracted at upload time: the BigIntAccumState cells of these rows depend on
+  // the accum mix and are computed on the host between the two phases (prove/witgen/mod.rs:186-207, byte_poly.rs:403-475)
+  struct BigIntCycle {
+    uint32_t row, poly_op, coeff;
+    uint8_t bytes[16];
+  };
+  std::vector<BigIntCycle> bigint;
   cudaEvent_t ready = nullptr;
 };
+
+namespace {
+// RawPreflightCycle / RawMemoryTransaction as the host hands them over (rv32im-sys/src/lib.rs:21-61)
+struct HostCycle {
+  uint32_t state, pc;
+  uint8_t major, minor, machine_mode, padding;
+  uint32_t user_cycle, txn_idx, paging_idx, bigint_idx, diff_count[2];
+};
+struct HostTxn {
+  uint32_t addr, cycle, word, prev_cycle, prev_word;
+};
+static_assert(sizeof(HostCycle) == 36 && sizeof(HostTxn) == 20, "preflight trace layout");
+constexpr uint32_t kMajorBigInt = 12;      // 7 + CycleState::BigIntEcall (40) / 8; minor 0 = the ecall cycle, 1 = a step
+constexpr uint32_t kPolyReset = 0, kPolyShift = 1, kPolySetTerm = 2, kPolyAddTotal = 3, kPolyCarry1 = 4, kPolyCarry2 = 5,
+                   kPolyEqZero = 6;
+// accum columns of BigIntAccumState: poly, term, total, four words each (kLayout_TopAccum.user._0.state; pinned by
+// tests/test_preflight.py::test_bigint_accum_columns)
+constexpr uint32_t kBigIntAccumCols[3] = {0, 4, 8};
+
+// what a bigint row carries into the accum phase: the 16 witness bytes and, for a step cycle, poly_op / coeff of the
+// verify-program word it executed - the first recorded transaction of the cycle (prove/witgen/bigint.rs:113-116)
+void collect_bigint_cycles(const r0b200_preflight_trace* t, size_t cycles, std::vector<r0b200_segment::BigIntCycle>& out) {
+  const HostCycle* cyc = static_cast<const HostCycle*>(t->cycles);
+  const HostTxn* txn = static_cast<const HostTxn*>(t->txns);
+  for (size_t r = 0; r < cycles; r++) {
+    if (cyc[r].major != kMajorBigInt) continue;
+    r0b200_segment::BigIntCycle b{};
+    b.row = (uint32_t)r;
+    R0_CHECK(t->bigint_bytes != nullptr && (size_t)cyc[r].bigint_idx + 16 <= t->bigint_bytes_len,
+             "segment_upload: bigint cycle without its 16 witness bytes");
+    memcpy(b.bytes, t->bigint_bytes + cyc[r].bigint_idx, 16);
+    if (cyc[r].minor == 0) {
+      b.poly_op = kPolyReset;
+      b.coeff = 0;
+    } else {
+      R0_CHECK(cyc[r].txn_idx < t->txns_len, "segment_upload: bigint step cycle without transactions");
+      const uint32_t insn = txn[cyc[r].txn_idx].word;
+      b.poly_op = (insn >> 24) & 0xf;
+      b.coeff = (insn >> 21) & 0x7;
+      R0_CHECK(b.poly_op <= kPolyEqZero, "segment_upload: invalid poly_op in bigint program");
+    }
+    out.push_back(b);
+  }
+}
+
+// BigIntAccum::step over the segment's bigint cycles at the mix point (Montgomery words; the last four of the accum
+// mix): fills the scatter arrays for the 12 cells of each row. Throws when the program's identity does not hold.
+void bigint_accum_cells(const std::vector<r0b200_segment::BigIntCycle>& rows, const uint32_t* mix, size_t mix_size, size_t cycles,
+                        std::vector<uint32_t>& index, std::vector<uint32_t>& offsets, std::vector<uint32_t>& values) {
+  const FpExt z{{mix[mix_size - 4], mix[mix_size - 3], mix[mix_size - 2], mix[mix_size - 1]}};
+  FpExt powers[17];
+  powers[0] = ext_one();
+  for (int i = 1; i < 17; i++) powers[i] = ext_mul(powers[i - 1], z);
+  FpExt neg_poly = ext_zero();
+  for (int i = 0; i < 16; i++) neg_poly = ext_add(neg_poly, ext_scale(powers[i], fp_encode(128)));
+  FpExt poly = ext_zero(), term = ext_one(), total = ext_zero();
+  index.assign(1, 0u);
+  for (const auto& b : rows) {
+    FpExt delta = ext_zero();
+    for (int i = 0; i < 16; i++) delta = ext_add(delta, ext_scale(powers[i], fp_encode(b.bytes[i])));
+    const FpExt new_poly = ext_add(poly, delta);
+    bool reset = false;
+    switch (b.poly_op) {
+      case kPolyReset: reset = true; break;
+      case kPolyShift: poly = ext_mul(new_poly, powers[16]); break;
+      case kPolySetTerm:
+        poly = ext_zero();
+        term = new_poly;
+        break;
+      case kPolyAddTotal:
+        total = ext_add(total, ext_mul(ext_scale(term, fp_sub(fp_encode(b.coeff), fp_encode(4))), new_poly));
+        poly = ext_zero();
+        term = ext_one();
+        break;
+      case kPolyCarry1: poly = ext_add(poly, ext_scale(ext_sub(delta, neg_poly), fp_encode(64 * 256))); break;
+      case kPolyCarry2: poly = ext_add(poly, ext_scale(delta, fp_encode(256))); break;
+      default: {  // EqZero
+        const FpExt goal = ext_add(total, ext_mul(new_poly, ext_sub(powers[1], ext_from_fp(fp_encode(256)))));
+        R0_CHECK((goal.c[0] | goal.c[1] | goal.c[2] | goal.c[3]) == 0, "accum: Invalid eqz in bigint accum");
+        reset = true;
+      }
+    }
+    if (reset) {
+      poly = ext_zero();
+      term = ext_one();
+      total = ext_zero();
+    }
+    const FpExt* regs[3] = {&poly, &term, &total};
+    for (int k = 0; k < 3; k++)
+      for (int j = 0; j < 4; j++) {
+        offsets.push_back((uint32_t)((kBigIntAccumCols[k] + j) * cycles + b.row));
+        values.push_back(regs[k]->c[j]);
+      }
+    index.push_back((uint32_t)offsets.size());
+  }
+}
+}  // namespace
 
 extern "C" void r0b200_segment_free(r0b200_segment* seg) {
   if (!seg) return;
@@ -725,6 +829,7 @@ extern "C" r0b200_err r0b200_segment_upload(r0b200_ctx* ctx, uint32_t po2, const
   seg->ctx = ctx;
   seg->po2 = po2;
   seg->global.assign(global_host, global_host + kRv32im.output_size);
+  collect_bigint_cycles(trace_host, cycles, seg->bigint);
   cudaStream_t cs = ctx->copy_stream;
   seg->trace = r0_trace_upload(ctx, trace_host, (uint32_t)cycles, cs);
   if (inj_index_len >= 2) {
@@ -781,6 +886,19 @@ static void prove_core_rv32im(r0b200_ctx* ctx, int hash, r0b200_segment* seg, ui
     NvtxRange r2("accumulate");
     accum = DevBuf(ctx, d.group_sizes[0] * cycles);
     r0_fill(ctx, accum.p, FP_INVALID, accum.words);
+    DevBuf bi_index, bi_offsets, bi_values;
+    std::vector<uint32_t> h_index, h_offsets, h_values;   // outlive the copies below (pageable: staged before return)
+    if (!seg->bigint.empty()) {
+      // inject BigIntAccumState backs (witgen/mod.rs:186-207): a function of the mix the transcript has just yielded
+      bigint_accum_cells(seg->bigint, p->mix.data(), d.mix_size, cycles, h_index, h_offsets, h_values);
+      bi_index = DevBuf(ctx, h_index.size());
+      bi_offsets = DevBuf(ctx, h_offsets.size());
+      bi_values = DevBuf(ctx, h_values.size());
+      R0_CUDA(cudaMemcpyAsync(bi_index.p, h_index.data(), h_index.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      R0_CUDA(cudaMemcpyAsync(bi_offsets.p, h_offsets.data(), h_offsets.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      R0_CUDA(cudaMemcpyAsync(bi_values.p, h_values.data(), h_values.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      r0_scatter_dev(ctx, accum.p, bi_index.p, h_index.size() - 1, bi_offsets.p, bi_values.p);
+    }
     R0_CUDA(cudaMemcpyAsync(d_mix.p, p->mix.data(), d.mix_size * 4, cudaMemcpyHostToDevice, ctx->stream));
     r0_accum_rv32im(ctx, seg->trace, data.p, accum.p, d_global.p, d_mix.p, /*sync_check=*/true);
     r0_eltwise_zeroize(ctx, accum.p, accum.words);

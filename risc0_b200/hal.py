@@ -531,13 +531,13 @@ class SegmentProver:
     def free_segment(self, segment):
         self.hal._l.r0b200_segment_free(segment[0])
 
-    def prove_core(self, pf):
+    def prove_core(self, pf, two_phase=False):
         """SegmentProverImpl::prove_core (rv32im/src/prove/hal/mod.rs:143-224) from a PreflightResults, everything on
         the device in one call (r0b200_prove_segment_rv32im). Returns (seal, roots, query positions, globals).
-        A segment with bigint cycles takes the protocol's own two-phase route instead (prove_begin -> mix -> host-built
-        BigIntAccum injector + step_accum on the device -> prove_finish), as include/r0b200.h prescribes for it."""
+        two_phase=True takes the protocol's own split through the Hal-level calls instead (WitnessGenerator, prove_begin
+        -> mix -> accum with the host-built BigIntAccum injector -> prove_finish): same seal."""
         hal = self.hal
-        if getattr(pf, "has_bigint", False):
+        if two_phase:
             wg = WitnessGenerator(hal, pf)
             try:
                 glob = wg.global_.view().copy()

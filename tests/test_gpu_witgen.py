@@ -103,16 +103,16 @@ def test_two_phase_with_device_accum(hal):
     assert np.array_equal(seal, want)
 
 
-def test_one_call_segment_path_refuses_bigint_segments(hal):
-    # r0b200_prove_segment cannot know the mix-dependent BigIntAccum cells (include/r0b200.h): step_accum finds them unset
-    # and the call fails loudly instead of producing a seal; the two-phase route (SegmentProver.prove_core picks it) works
+def test_bigint_segment_one_call_equals_two_phase(hal):
+    # the one-call path (r0b200_segment_upload / r0b200_prove_segment) evaluates the mix-dependent BigIntAccum cells itself,
+    # from the trace; the Hal-level two-phase route gets them from the host mirror (PreflightResults.bigint_accum_injector):
+    # same seal, and the verifier accepts it including the constraint check
     pf = PF.PreflightResults(seg("bigint"), (51, 52, 53, 54))
     prover = SegmentProver(hal)
-    with pytest.raises(Exception) as ei:
-        prover.prove_segment(prover.upload_segment(pf))
-    assert "unset" in str(ei.value).lower() or "accum" in str(ei.value).lower()
-    seal = prover.prove_core(pf)[0]                    # the context is still usable, and the right route gives a valid seal
-    assert O.verify_with_validity(seal)[1]
+    one = prover.prove_segment(prover.upload_segment(pf))[0]
+    two = prover.prove_core(pf, two_phase=True)[0]
+    assert np.array_equal(one, two)
+    assert O.verify_with_validity(one)[1]
 
 
 def test_verifier_rejects_a_witness_that_violates_constraints(hal):

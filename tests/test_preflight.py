@@ -9,6 +9,8 @@
   * the step functions generated from the circuit IR (tools/gen_witgen.py; here in a host build) give the reference's
     data and accum matrices word for word - the same text is what csrc/witgen*.cu compiles for the device.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -207,6 +209,16 @@ def test_bigint_ecall_guest(seed):
     with pytest.raises(RuntimeError) as ei:
         W.host_accum(pf, glob, data, mix, accum=accum)
     assert "Inconsistent set" in str(ei.value) or "eqz" in str(ei.value)
+
+
+def test_bigint_accum_columns():
+    # csrc/prover.cu hard-codes where BigIntAccumState lives in the accum matrix (kBigIntAccumCols) and the bigint major
+    A = "kLayout_TopAccum"
+    assert [PF.layout_col(A, "user._0.state.%s._super" % n) for n in ("poly", "term", "total")] == [0, 4, 8]
+    assert 7 + PF.CS.BigIntEcall // 8 == 12 and PF.CS.BigIntEcall % 8 == 0 and PF.CS.BigIntStep % 8 == 1
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "risc0_b200", "csrc", "prover.cu")).read()
+    assert re.search(r"kBigIntAccumCols\[3\] = \{0, 4, 8\}", src) and "kMajorBigInt = 12" in src
 
 
 def test_user_mode_guest_with_kernel_traps():
