@@ -2239,24 +2239,32 @@ def sha2_guest(message=b"abc", loops=3):
     return MemoryImage.new_kernel(entry, image)
 
 
-BIGINT_GUEST_OUT_ADDR = 0x00501060
+BIGINT_GUEST_OUT_ADDR = 0x005010c0
 
 
-def bigint_modmul_guest(blob, a, b, n, loops=3):
-    """machine-mode guest that runs a bigint2 `modmul_256` blob (header: nondet / verify / consts / temp sizes in words,
-    then the bibc program, the verify program and the constants; zkvm/platform/src/syscall.rs:1044-1115 shows how a guest
-    lays the registers out): a, b, n are 256-bit operands at a1, a2, a3, the product a * b mod n lands at a4
-    (BIGINT_GUEST_OUT_ADDR), the quotient in the scratch space sp points at."""
+def bigint_guest(blob, inputs, outputs, loops=3):
+    """machine-mode guest that runs a bigint2 blob (header: nondet / verify / consts / temp sizes in words, then the bibc
+    program, the verify program and the constants; zkvm/platform/src/syscall.rs:1044-1115 shows how a guest lays the
+    registers out). inputs: {register: bytes} operand regions (a program addresses them as register + 16-byte offset),
+    outputs: {register: size in bytes} result regions; the scratch space the blob asks for hangs off sp.
+    Returns (image, {register: byte address})."""
     import struct
     nondet_size, verify_size, consts_size, temp_size = struct.unpack_from("<4I", blob, 0)
     assert len(blob) == 16 + 4 * (nondet_size + verify_size + consts_size)
-    blob_addr, a_addr, temp_addr = 0x00500000, 0x00501000, 0x00501100
+    blob_addr, next_addr = 0x00500000, 0x00501000
     asm = Assembler()
     for i in range(len(blob) // 4):
         asm.word(blob_addr + 4 * i, int.from_bytes(blob[4 * i:4 * i + 4], "little"))
-    for k, v in enumerate((a, b, n)):
-        for i in range(8):
-            asm.word(a_addr + 32 * k + 4 * i, (v >> (32 * i)) & M32)
+    where = {}
+    for reg, data in inputs.items():
+        assert len(data) % 16 == 0
+        where[reg] = next_addr
+        for i in range(len(data) // 4):
+            asm.word(next_addr + 4 * i, int.from_bytes(data[4 * i:4 * i + 4], "little"))
+        next_addr += len(data) + 32
+    for reg, size in list(outputs.items()) + [(REG_SP, max(16, 4 * temp_size))]:
+        where[reg] = next_addr
+        next_addr += -(-size // 16) * 16 + 32
     a4, a5, t4 = 14, 15, 29
     asm.addi(a4, 0, 0)
     asm.li(a5, loops)
@@ -2267,16 +2275,21 @@ def bigint_modmul_guest(blob, a, b, n, loops=3):
     asm.li(REG_T1, blob_addr + 16)
     asm.li(REG_T2, blob_addr + 16 + 4 * nondet_size)
     asm.li(REG_T3, blob_addr + 16 + 4 * (nondet_size + verify_size))
-    asm.li(REG_A1, a_addr)
-    asm.li(REG_A2, a_addr + 32)
-    asm.li(REG_A3, a_addr + 64)
-    asm.li(REG_A4, BIGINT_GUEST_OUT_ADDR)
-    asm.li(REG_SP, temp_addr)
+    for reg, addr in where.items():
+        asm.li(reg, addr)
     asm.li(REG_A7, HOST_ECALL_BIGINT)
     asm.ecall()
-    asm.li(t4, BIGINT_GUEST_OUT_ADDR)
-    asm.load(2, a5, t4, 0)
-    asm.load(2, a5, t4, 28)
+    first_out = where[next(iter(outputs))]
+    asm.li(t4, first_out)
+    asm.load(2, a5, t4, 0)                              # the result is read back by an ordinary instruction
     asm.host_terminate(0, 0)
     entry, image = asm.program()
-    return MemoryImage.new_kernel(entry, image)
+    return MemoryImage.new_kernel(entry, image), where
+
+
+def bigint_modmul_guest(blob, a, b, n, loops=3):
+    """`modmul_256`: a, b, n are 256-bit operands at a1, a2, a3, the product a * b mod n lands at a4"""
+    image, where = bigint_guest(blob, {REG_A1: a.to_bytes(32, "little"), REG_A2: b.to_bytes(32, "little"),
+                                       REG_A3: n.to_bytes(32, "little")}, {REG_A4: 32}, loops)
+    assert where[REG_A4] == BIGINT_GUEST_OUT_ADDR
+    return image

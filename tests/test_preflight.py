@@ -211,6 +211,58 @@ def test_bigint_ecall_guest(seed):
     assert "Inconsistent set" in str(ei.value) or "eqz" in str(ei.value)
 
 
+def _golden_blob(name):
+    return open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bigint_%s.blob" % name), "rb").read()
+
+
+P256 = 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff
+P384 = 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffeffffffff0000000000000000ffffffff
+
+
+@pytest.mark.parametrize("name", ["modinv_256", "modsub_256", "modadd_256", "modmul_384", "extfield_deg2_mul_256"])
+def test_bigint_blobs_of_the_reference(name):
+    """more of the reference's bigint2 field programs (risc0/bigint2/src/field/*.blob, copied as fixtures): Inv and the
+    constants section (modinv), negative intermediates (modsub), 384-bit operands = three chunks per value (modmul_384), a
+    214-word verify program with 39 scratch chunks (extfield_deg2_mul). Each trace is accepted by the reference's compiled
+    witgen and satisfies every constraint; where the function is a plain modular one the result is checked too."""
+    rng = np.random.default_rng(sum(name.encode()))
+    A1, A2, A3, A4, A5 = PF.REG_A1, PF.REG_A2, PF.REG_A3, PF.REG_A4, 15
+
+    def rnd(n):
+        return int.from_bytes(rng.bytes(48), "little") % n
+
+    if name == "modinv_256":
+        a = rnd(P256)
+        inputs, outputs, want = {A1: a.to_bytes(32, "little"), A2: P256.to_bytes(32, "little")}, {A3: 32}, pow(a, -1, P256)
+    elif name in ("modsub_256", "modadd_256"):
+        a, b = rnd(P256), rnd(P256)
+        inputs = {A1: a.to_bytes(32, "little"), A2: b.to_bytes(32, "little"), A3: P256.to_bytes(32, "little")}
+        outputs, want = {A4: 32}, ((a - b) if name == "modsub_256" else (a + b)) % P256
+    elif name == "modmul_384":
+        a, b = rnd(P384), rnd(P384)
+        inputs = {A1: a.to_bytes(48, "little"), A2: b.to_bytes(48, "little"), A3: P384.to_bytes(48, "little")}
+        outputs, want = {A4: 48}, a * b % P384
+    else:   # (a0 + a1 x)(b0 + b1 x) mod (x^2 - nr), nr at a3 (two chunks), modulus at a4
+        vals = [rnd(P256) for _ in range(6)]
+        pack = lambda lo, hi: lo.to_bytes(32, "little") + hi.to_bytes(32, "little")
+        inputs = {A1: pack(vals[0], vals[1]), A2: pack(vals[2], vals[3]), A3: pack(vals[4], vals[5]),
+                  A4: P256.to_bytes(32, "little")}
+        outputs, want = {A5: 64}, None
+    image, where = PF.bigint_guest(_golden_blob(name), inputs, outputs)
+    segs = PF.execute(image, segment_po2=14)
+    assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
+    pf, _, _, _ = check_segment(segs[0], seed=7)
+    assert pf.has_bigint
+    if want is not None:
+        reg, size = next(iter(outputs.items()))
+        out = {}
+        for t in pf.txns:
+            addr = int(t["addr"]) * 4
+            if where[reg] <= addr < where[reg] + size and int(t["cycle"]) % 2 == 1:
+                out[addr] = int(t["word"])
+        assert sum(out[where[reg] + 4 * i] << (32 * i) for i in range(size // 4)) == want
+
+
 def test_bigint_accum_columns():
     # csrc/prover.cu hard-codes where BigIntAccumState lives in the accum matrix (kBigIntAccumCols) and the bigint major
     A = "kLayout_TopAccum"
