@@ -3,6 +3,7 @@
 
 Copies the reference's golden STARK seal and records the known-answer vectors its own unit tests assert:
   proof.bin    <- risc0/zkp/src/verify/proof.bin            (verify_v3_stark_proof, verify/mod.rs:713-726)
+  bigint_*.blob <- risc0/bigint2/src/field/*.blob            (bigint2 programs the bigint-ecall test guests execute)
   kats.json    <- literals asserted in:
       risc0/core/src/field/baby_bear.rs:893-894 (5^1000), :815-853 (FpExt linear)
       risc0/zkp/src/core/hash/poseidon2/mod.rs:330-351 (permutation), :354-401 (hash 32 / 17 elems)
@@ -23,6 +24,10 @@ def ints(s):
     return [int(x, 16) if x.lower().startswith("0x") else int(x) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", s)]
 
 shutil.copyfile(os.path.join(REF, "risc0/zkp/src/verify/proof.bin"), os.path.join(HERE, "proof.bin"))
+# bigint2 programs (blob = header + bibc 'nondet' program + verify program + constants) that the bigint-ecall guests of
+# tests/test_preflight.py / tests/test_gpu_witgen.py run: risc0/bigint2/src/field/<name>.blob -> bigint_<name>.blob
+for name in ("modmul_256", "modinv_256", "modsub_256", "modadd_256", "modmul_384", "extfield_deg2_mul_256"):
+    shutil.copyfile(os.path.join(REF, "risc0/bigint2/src/field/%s.blob" % name), os.path.join(HERE, "bigint_%s.blob" % name))
 
 bb = read("risc0/core/src/field/baby_bear.rs")
 m = re.search(r"Elem::new\(5\)\.pow\(1000\),\s*Elem::new\((\d+)\)", bb)
