@@ -129,6 +129,40 @@ def all_insn_guest():
     return PF.MemoryImage.new_kernel(entry, image)
 
 
+def test_reference_kernel_basic_and_multi_read():
+    """execute/testutil.rs kernel::basic (terminate only; witgen/tests.rs:52-55) and kernel::multi_read (:122-146): host
+    reads of 0 ... 101 bytes at all four alignments under NullSyscall (byte i of a read is i), each byte loaded back and
+    compared by the guest itself - a wrong byte runs into the illegal instruction and the executor raises"""
+    a = PF.Assembler()
+    a.host_terminate(0, 0)
+    entry, image = a.program()
+    segs = PF.execute(PF.MemoryImage.new_kernel(entry, image), segment_po2=14)
+    assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
+    check_segment(segs[0], seed=8)
+
+    t0, t1, t2 = 5, 6, 7
+    ptr = 0x00500000
+    a = PF.Assembler()
+    a.li(t0, ptr)
+    for i in range(4):
+        for ln in (0, 1, 2, 3, 4, 5, 7, 13, 19, 40, 101):
+            a.host_ecall_read(0, ptr + i, ln)
+            for k in range(ln):
+                a.lb(t1, t0, i + k)
+                a.li(t2, k)
+                a.beq(t1, t2, 8)
+                a.text.append(0)          # die()
+    a.host_terminate(0, 0)
+    entry, image = a.program()
+    segs = PF.execute(PF.MemoryImage.new_kernel(entry, image), segment_po2=16)
+    assert segs[-1].terminate_state == (0, 0) and all(sg.terminate_state is None for sg in segs[:-1])
+    kinds = set()
+    for sg in segs:                                   # the guest is long enough to split: every segment is checked
+        pf, _, _, _ = check_segment(sg, seed=9)
+        kinds |= set(zip(pf.cycles["major"].tolist(), pf.cycles["minor"].tolist()))
+    assert {(8, 2), (8, 4), (8, 5)} <= kinds          # HostReadSetup, HostReadBytes, HostReadWords
+
+
 def test_every_instruction_kind_and_host_read():
     segs = PF.execute(all_insn_guest(), segment_po2=14)
     assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
