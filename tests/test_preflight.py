@@ -129,6 +129,32 @@ def all_insn_guest():
     return PF.MemoryImage.new_kernel(entry, image)
 
 
+def test_reference_executor_tests_basic_and_system_split():
+    """execute/tests.rs:23-56 `basic` and :58-95 `system_split`, assertion for assertion, on the executor restatement"""
+    a = PF.Assembler()
+    a.host_terminate(0, 0)
+    entry, image = a.program()
+    img = PF.MemoryImage.new_kernel(entry, image)
+    pre = img.image_id()
+    segs = PF.execute(img, segment_po2=20)
+    assert len(segs) == 1
+    s = segs[0]
+    assert s.pre_state == pre and s.post_state != pre
+    assert s.input == (0,) * 8 and s.output == (0,) * 8 and s.terminate_state == (0, 0)
+    assert s.read_record == [] and s.write_record == []
+    assert s.suspend_cycle == len(image) + 1
+
+    img = PF.simple_loop_kernel(2000)
+    pre = img.image_id()
+    segs = PF.execute(img, segment_po2=13, max_insn_cycles=100)     # testutil::MIN_CYCLES_PO2 = 13
+    assert len(segs) == 2
+    assert segs[0].pre_state == pre and segs[0].post_state != pre
+    assert segs[0].input == (0,) * 8 and segs[0].output is None and segs[0].terminate_state is None
+    assert segs[1].pre_state == segs[0].post_state and segs[1].post_state != segs[1].pre_state
+    assert segs[1].input == (0,) * 8 and segs[1].output == (0,) * 8 and segs[1].terminate_state == (0, 0)
+    assert segs[0].read_record == [] and segs[0].write_record == []
+
+
 def test_reference_kernel_basic_and_multi_read():
     """execute/testutil.rs kernel::basic (terminate only; witgen/tests.rs:52-55) and kernel::multi_read (:122-146): host
     reads of 0 ... 101 bytes at all four alignments under NullSyscall (byte i of a read is i), each byte loaded back and
