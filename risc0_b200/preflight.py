@@ -784,8 +784,15 @@ class Machine:
             c.pc = (c.pc + 4) & M32
             c.on_ecall_cycle(CS.MachineEcall, CS.PoseidonEntry, 0, 0, 0)
             m = MACHINE_REGS_ADDR // 4
-            p2 = Poseidon2State.new_ecall(c.load_u32(RECORD, m + REG_A0), c.load_u32(RECORD, m + REG_A1),
-                                          c.load_u32(RECORD, m + REG_A2), c.load_u32(RECORD, m + REG_A3))
+            # Address convention: this snapshot's Rust (execute/poseidon2.rs:285-293, zkvm/platform syscall.rs:482-505)
+            # hands the three registers over as WORD addresses, but the circuit it ships (steps.cpp:6059-6069 ReadAddr:
+            # high * 2^14 + low / 4) takes them as BYTE addresses and divides by four - a trace built the Rust way is
+            # rejected by the reference's own compiled witgen ("Inconsistent set" at stateAddr / bufOutAddr). The
+            # circuit is what the witness generator implements, so the restatement follows the circuit.
+            regs = [c.load_u32(RECORD, m + r) for r in (REG_A0, REG_A1, REG_A2, REG_A3)]
+            if any(r % 4 for r in regs[:3]):
+                raise ValueError("poseidon2 ecall: unaligned address")
+            p2 = Poseidon2State.new_ecall(regs[0] // 4, regs[1] // 4, regs[2] // 4, regs[3])
             p2.rest(c, CS.Decode)
             return False
         if which == HOST_ECALL_SHA2:          # r0vm.rs:559-571
@@ -2293,3 +2300,38 @@ def bigint_modmul_guest(blob, a, b, n, loops=3):
                                        REG_A3: n.to_bytes(32, "little")}, {REG_A4: 32}, loops)
     assert where[REG_A4] == BIGINT_GUEST_OUT_ADDR
     return image
+
+
+P2_GUEST_OUT_ADDR, P2_GUEST_STATE_ADDR = 0x00502000, 0x00502100
+
+
+def poseidon2_ecall_guest(words, is_elem, state=None, expect=None):
+    """machine-mode guest that absorbs `words` with the poseidon2 ecall (r0vm.rs:545-557, execute/poseidon2.rs:56-72,
+    285-293; registers carry byte addresses, see Machine._machine_ecall): is_elem - 16 field elements per block, else 8 words = 16 half-words per
+    block; state - 8 capacity words loaded before / stored after (a0 != 0); expect - a digest already in memory that
+    the ecall checks instead of storing (PFLAG_CHECK_OUT)."""
+    per_block = 16 if is_elem else 8
+    assert len(words) % per_block == 0
+    in_addr = 0x00501000
+    asm = Assembler()
+    for i, w in enumerate(words):
+        asm.word(in_addr + 4 * i, w)
+    if state is not None:
+        for i, w in enumerate(state):
+            asm.word(P2_GUEST_STATE_ADDR + 4 * i, w)
+    if expect is not None:
+        for i, w in enumerate(expect):
+            asm.word(P2_GUEST_OUT_ADDR + 4 * i, w)
+    a4, t4 = 14, 29
+    asm.addi(a4, 0, 3)
+    asm.li(REG_A0, P2_GUEST_STATE_ADDR if state is not None else 0)
+    asm.li(REG_A1, in_addr)
+    asm.li(REG_A2, P2_GUEST_OUT_ADDR)
+    asm.li(REG_A3, (len(words) // per_block) | (PFLAG_IS_ELEM if is_elem else 0) | (PFLAG_CHECK_OUT if expect is not None else 0))
+    asm.li(REG_A7, HOST_ECALL_POSEIDON2)
+    asm.ecall()
+    asm.li(t4, P2_GUEST_OUT_ADDR)
+    asm.load(2, a4, t4, 0)
+    asm.host_terminate(0, 0)
+    entry, image = asm.program()
+    return MemoryImage.new_kernel(entry, image)

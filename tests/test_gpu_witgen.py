@@ -27,6 +27,9 @@ def segments():
     out["user_mode"] = PF.execute(PF.user_mode_guest(30), segment_po2=14)[0]
     out["sha2"] = PF.execute(PF.sha2_guest(bytes(range(200))), segment_po2=14)[0]   # 4 blocks through the sha2 ecall
     out["bigint"] = PF.execute(bigint_guest(2)[0], segment_po2=14)[0]               # modmul_256 through the bigint ecall
+    rng = np.random.default_rng(77)                                                  # guest-invoked poseidon2 ecall with state
+    out["p2_ecall"] = PF.execute(PF.poseidon2_ecall_guest([int(x) for x in rng.integers(0, 1 << 32, 24)], 0,
+                                                          [int(x) for x in rng.integers(0, PF.P, 8)]), segment_po2=14)[0]
     split = PF.execute(PF.simple_loop_kernel(4000), segment_po2=13)
     out["split_first"], out["split_second"] = split[0], split[1]
     return out
@@ -42,7 +45,8 @@ def seg(name):
     return SEGS[name]
 
 
-@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second", "user_mode", "sha2", "bigint"])
+@pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second", "user_mode", "sha2", "bigint",
+                                  "p2_ecall"])
 def test_device_witgen_and_accum_match_reference(hal, name):
     pf = PF.PreflightResults(seg(name), (11, 12, 13, 14))
     want_glob, want_data = W.ref_generate_witness(pf)

@@ -333,6 +333,48 @@ def test_bigint_accum_columns():
     assert re.search(r"kBigIntAccumCols\[3\] = \{0, 4, 8\}", src) and "kMajorBigInt = 12" in src
 
 
+def _p2_sponge(words, is_elem, state):
+    cells = [0] * 24
+    if state is not None:
+        cells[16:24] = list(state)
+    per_block = 16 if is_elem else 8
+    for b in range(0, len(words), per_block):
+        blk = words[b:b + per_block]
+        cells[:16] = list(blk) if is_elem else [h for w in blk for h in (w & 0xffff, w >> 16)]
+        cells = list(PF.poseidon2_mix(cells))
+    return cells
+
+
+@pytest.mark.parametrize("is_elem,with_state,check", [(1, False, False), (0, True, False), (1, True, True)])
+def test_poseidon2_ecall_guest(is_elem, with_state, check):
+    """the guest-invoked poseidon2 ecall (execute/poseidon2.rs:56-148,285-293; the same cycles page-in / page-out use, here
+    with mode 1 / READ transactions): element and half-word inputs, the optional capacity state, and the check-only form.
+    The digest is the sponge computed independently from the permutation; the reference's witgen accepts the trace."""
+    rng = np.random.default_rng(31 + is_elem + 2 * with_state)
+    n_blocks = 3
+    words = [int(x) for x in (rng.integers(0, PF.P, 16 * n_blocks) if is_elem else rng.integers(0, 1 << 32, 8 * n_blocks))]
+    state = [int(x) for x in rng.integers(0, PF.P, 8)] if with_state else None
+    want = _p2_sponge(words, is_elem, state)
+    image = PF.poseidon2_ecall_guest(words, is_elem, state, expect=want[:8] if check else None)
+    segs = PF.execute(image, segment_po2=14)
+    assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
+    pf, _, _, _ = check_segment(segs[0], seed=10)
+    stored = {}
+    for t in pf.txns:
+        addr = int(t["addr"]) * 4
+        if int(t["cycle"]) % 2 == 1:
+            stored[addr] = int(t["word"])
+    if not check:
+        assert [stored[PF.P2_GUEST_OUT_ADDR + 4 * i] for i in range(8)] == want[:8]
+    if with_state:
+        assert [stored[PF.P2_GUEST_STATE_ADDR + 4 * i] for i in range(8)] == want[16:24]
+    if check:   # a wrong expected digest makes the executor fail, as the reference's does ("poseidon2 check failed")
+        bad = list(want[:8])
+        bad[3] ^= 1
+        with pytest.raises(ValueError):
+            PF.execute(PF.poseidon2_ecall_guest(words, is_elem, state, expect=bad), segment_po2=14)
+
+
 def test_user_mode_guest_with_kernel_traps():
     # user-mode code under a machine-mode kernel: mret into user mode, user ecall -> kernel dispatch -> terminate
     segs = PF.execute(PF.user_mode_guest(30), segment_po2=14)
