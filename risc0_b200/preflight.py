@@ -1630,8 +1630,9 @@ assert CYCLE_DTYPE.itemsize == 36 and TXN_DTYPE.itemsize == 20
 
 
 class _Preflight:
-    def __init__(self, segment, rand_z):
+    def __init__(self, segment, rand_z, write_record_off_by_one=True):
         self.segment = segment
+        self.write_record_off_by_one = write_record_off_by_one
         self.rand_z = tuple(int(x) for x in rand_z)
         self.cycles = []     # [state, pc, major, minor, machine_mode, user_cycle, txn_idx, paging_idx, bigint_idx, d0, d1]
         self.backs = []      # None | ("ecall", s0, s1, s2) | ("p2", Poseidon2State) | ("sha2", Sha2State) | ("bigint", BigIntState)
@@ -1712,8 +1713,13 @@ class _Preflight:
         return rec
 
     def host_write(self, fd, data):
+        # preflight.rs:666-674 increments cur_write BEFORE indexing the record (sic), so the reference's own preflight
+        # cannot get through a segment whose last ecall is a host write. write_record_off_by_one=False reads the entry
+        # the executor recorded for THIS write instead, which is what lets the HostWrite arm of the circuit be exercised.
         self.cur_write += 1
-        return self.segment.write_record[self.cur_write]   # (sic) preflight.rs:681-686
+        if self.write_record_off_by_one:
+            return self.segment.write_record[self.cur_write]
+        return self.segment.write_record[self.cur_write - 1]
 
     # -- memory
     def load_u32(self, op, waddr):
@@ -1938,8 +1944,8 @@ class Injector:
 class PreflightResults:
     """witgen/mod.rs:55-88: what prove_core starts from. cycles / txns are the RawPreflightTrace arrays."""
 
-    def __init__(self, segment, rand_z):
-        pf = _Preflight(segment, rand_z)
+    def __init__(self, segment, rand_z, write_record_off_by_one=True):
+        pf = _Preflight(segment, rand_z, write_record_off_by_one)
         self.table_split_cycle = pf.run()
         self.po2 = segment.po2
         self.rows = 1 << segment.po2

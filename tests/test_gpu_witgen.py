@@ -9,7 +9,7 @@ import oracle_lib as O
 import witgen_ref as W
 from risc0_b200 import B200Hal, SegmentProver, WitnessGenerator
 from risc0_b200 import preflight as PF
-from test_preflight import all_insn_guest, bigint_guest
+from test_preflight import all_insn_guest, bigint_guest, host_write_guest
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (W.have_ref() and O.have_ref()), reason="oracle/_ref not built")]
 
@@ -27,6 +27,7 @@ def segments():
     out["user_mode"] = PF.execute(PF.user_mode_guest(30), segment_po2=14)[0]
     out["sha2"] = PF.execute(PF.sha2_guest(bytes(range(200))), segment_po2=14)[0]   # 4 blocks through the sha2 ecall
     out["bigint"] = PF.execute(bigint_guest(2)[0], segment_po2=14)[0]               # modmul_256 through the bigint ecall
+    out["host_write"] = PF.execute(host_write_guest(), segment_po2=14)[0]
     rng = np.random.default_rng(77)                                                  # guest-invoked poseidon2 ecall with state
     out["p2_ecall"] = PF.execute(PF.poseidon2_ecall_guest([int(x) for x in rng.integers(0, 1 << 32, 24)], 0,
                                                           [int(x) for x in rng.integers(0, PF.P, 8)]), segment_po2=14)[0]
@@ -46,9 +47,10 @@ def seg(name):
 
 
 @pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second", "user_mode", "sha2", "bigint",
-                                  "p2_ecall"])
+                                  "p2_ecall", "host_write"])
 def test_device_witgen_and_accum_match_reference(hal, name):
-    pf = PF.PreflightResults(seg(name), (11, 12, 13, 14))
+    # (host_write: with the write record indexed as the executor wrote it, see tests/test_preflight.py::test_host_write_guest)
+    pf = PF.PreflightResults(seg(name), (11, 12, 13, 14), write_record_off_by_one=name != "host_write")
     want_glob, want_data = W.ref_generate_witness(pf)
     wg = WitnessGenerator(hal, pf)
     assert np.array_equal(wg.global_.view(), want_glob)

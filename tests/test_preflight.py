@@ -129,6 +129,41 @@ def all_insn_guest():
     return PF.MemoryImage.new_kernel(entry, image)
 
 
+def host_write_guest():
+    a = PF.Assembler()
+    a.li(5, 0x00500000)
+    a.li(6, 0x64636261)
+    a.sw(6, 5, 0)
+    for fd, ptr, ln in ((1, 0x00500000, 4), (2, 0x00500001, 3), (1, 0x00500000, 0)):
+        a.li(PF.REG_A7, PF.HOST_ECALL_WRITE)
+        a.li(PF.REG_A0, fd)
+        a.li(PF.REG_A1, ptr)
+        a.li(PF.REG_A2, ln)
+        a.ecall()
+    a.host_terminate(0, 0)
+    entry, image = a.program()
+    return PF.MemoryImage.new_kernel(entry, image)
+
+
+def test_host_write_guest():
+    """the HostWrite arm. The reference's preflight reads its write record one entry too far (preflight.rs:666-674), so,
+    mirrored faithfully, a segment with host writes does not get through preflight - asserted here; with the entry that
+    belongs to the write, the reference's compiled witgen accepts the trace and every constraint holds."""
+    seg = PF.execute(host_write_guest(), segment_po2=14)[0]
+    assert seg.write_record == [4, 3, 0]
+    with pytest.raises(IndexError):
+        PF.PreflightResults(seg, (5, 6, 7, 8))
+    pf = PF.PreflightResults(seg, (5, 6, 7, 8), write_record_off_by_one=False)
+    glob, data = W.ref_generate_witness(pf)
+    glob2, data2 = W.host_generate_witness(pf)
+    assert np.array_equal(glob, glob2) and np.array_equal(data, data2)
+    mix, poly_mix = mixes(11)
+    accum = W.ref_accum(pf, glob, data, mix)
+    assert np.array_equal(accum, W.host_accum(pf, glob, data, mix))
+    assert O.rv32im_check_constraints(accum, data, mix, glob, poly_mix, pf.po2) == (0, None)
+    assert (8, 3) in set(zip(pf.cycles["major"].tolist(), pf.cycles["minor"].tolist()))
+
+
 def test_reference_executor_tests_basic_and_system_split():
     """execute/tests.rs:23-56 `basic` and :58-95 `system_split`, assertion for assertion, on the executor restatement"""
     a = PF.Assembler()
