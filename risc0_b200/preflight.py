@@ -1567,7 +1567,7 @@ class _ExecCtx:
 
 
 def execute(image, segment_po2=20, max_insn_cycles=None, max_cycles=1 << 24, input_digest=(0,) * 8, read_fn=None,
-            write_fn=None, max_segments=None):
+            write_fn=None, max_segments=None, povw_nonce=None):
     """Executor::run (executor.rs:209-405): runs the guest, returns the list of Segments. NullSyscall-style defaults."""
     if max_insn_cycles is None:
         max_insn_cycles = MAX_INSN_CYCLES if segment_po2 >= 15 else MAX_INSN_CYCLES_LOWER_PO2
@@ -1597,7 +1597,8 @@ def execute(image, segment_po2=20, max_insn_cycles=None, max_cycles=1 << 24, inp
                                 input=ctx.input_digest, output=ctx.output_digest, terminate_state=ctx.terminate_state,
                                 read_record=ctx.read_record, write_record=ctx.write_record, suspend_cycle=ctx.user_cycles,
                                 paging_cycles=ctx.pager.cycles, po2=po2, index=len(segments),
-                                segment_threshold=threshold, povw_nonce=None))
+                                segment_threshold=threshold,
+                                povw_nonce=tuple(povw_nonce) if povw_nonce is not None else None))
         ctx.read_record, ctx.write_record = [], []
 
     m.resume()

@@ -129,6 +129,20 @@ def all_insn_guest():
     return PF.MemoryImage.new_kernel(entry, image)
 
 
+def test_segment_with_povw_nonce():
+    """a segment that carries a proof-of-verifiable-work nonce (Segment::povw_nonce; preflight.rs:586-589 serves the nonce
+    words from the special address range, witgen/mod.rs builds the povwNonce globals): accepted, constraints hold, and the
+    nonce is what the globals say"""
+    nonce = (0x11111111, 0x22222222, 0x33333333, 0x44444444, 0x55555555, 0x66666666, 0x77777777, 0x12345678)
+    seg = PF.execute(PF.simple_loop_kernel(50), segment_po2=14, povw_nonce=nonce)[0]
+    pf, glob, _, _ = check_segment(seg, seed=12)
+    rinv = pow(1 << 32, -1, PF.P)
+    G = "kLayoutGlobal"
+    got = tuple((int(glob[PF.layout_col(G, "povwNonce.values[%d].low._super" % i)]) * rinv % PF.P) |
+                ((int(glob[PF.layout_col(G, "povwNonce.values[%d].high._super" % i)]) * rinv % PF.P) << 16) for i in range(8))
+    assert got == nonce
+
+
 def host_write_guest():
     a = PF.Assembler()
     a.li(5, 0x00500000)
