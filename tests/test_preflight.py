@@ -129,6 +129,40 @@ def all_insn_guest():
     return PF.MemoryImage.new_kernel(entry, image)
 
 
+def test_input_output_digests_and_exit_codes():
+    """a guest that reads its input digest, writes an output digest and terminates with (a0, a1) = (2, 7): the witness
+    generator's output globals (output, termA0 / termA1, stateOut) come out as the executor's claim says"""
+    a = PF.Assembler()
+    t0, t1 = 5, 6
+    a.li(t0, PF.GLOBAL_OUTPUT_ADDR)
+    for i in range(8):
+        a.li(t1, 0x01010101 * (i + 1))
+        a.sw(t1, t0, 4 * i)
+    a.li(t0, PF.GLOBAL_INPUT_ADDR)
+    a.load(2, t1, t0, 12)
+    a.host_terminate(2, 7)
+    entry, image = a.program()
+    inp = tuple(0xa0000000 + i for i in range(8))
+    seg = PF.execute(PF.MemoryImage.new_kernel(entry, image), segment_po2=14, input_digest=inp)[0]
+    assert seg.terminate_state == (2, 7) and seg.input == inp
+    assert seg.output == tuple(0x01010101 * (i + 1) for i in range(8))
+    pf, glob, _, _ = check_segment(seg, seed=13)
+    rinv = pow(1 << 32, -1, PF.P)
+    G = "kLayoutGlobal"
+
+    def cell(path):
+        return int(glob[PF.layout_col(G, path)]) * rinv % PF.P
+
+    def digest(name):
+        return tuple(cell("%s.values[%d].low._super" % (name, i)) | (cell("%s.values[%d].high._super" % (name, i)) << 16)
+                     for i in range(8))
+
+    assert digest("output") == seg.output and digest("input") == inp
+    assert digest("stateIn") == tuple(seg.pre_state) and digest("stateOut") == tuple(seg.post_state)
+    assert cell("isTerminate._super") == 1
+    assert (cell("termA0low._super") | (cell("termA0high._super") << 16), cell("termA1low._super") | (cell("termA1high._super") << 16)) == (2, 7)
+
+
 def test_segment_with_povw_nonce():
     """a segment that carries a proof-of-verifiable-work nonce (Segment::povw_nonce; preflight.rs:586-589 serves the nonce
     words from the special address range, witgen/mod.rs builds the povwNonce globals): accepted, constraints hold, and the
