@@ -129,6 +129,58 @@ def all_insn_guest():
     return PF.MemoryImage.new_kernel(entry, image)
 
 
+@pytest.mark.parametrize("kind", ["illegal", "misaligned_load", "misaligned_store", "load_fault"])
+def test_user_traps_reach_the_kernel_handler(kind):
+    """executor only: a user-mode fault enters the kernel through TRAP_DISPATCH_ADDR[cause] with MEPC = the faulting pc
+    (r0vm.rs:587-597,647-665). Neither the reference's preflight (its `trap` hook is the default no-op) nor the circuit
+    gives the trapping instruction a cycle, so such a segment is not provable there either - the generated step functions
+    reject the trace, which is asserted too."""
+    a4, a5, t0, t1 = 14, 15, 5, 6
+    user = PF.Assembler()
+    user.addi(a4, 0, 0)
+    user.li(a5, 5)
+    user.addi(a4, a4, 1)
+    user.blt(a4, a5, -4)
+    if kind == "illegal":
+        user.text.append(0)
+    elif kind == "misaligned_load":
+        user.li(t0, 0x00500001)
+        user.load(2, t1, t0, 0)
+    elif kind == "misaligned_store":
+        user.li(t0, 0x00500002)
+        user.sw(t1, t0, 0)
+    else:
+        user.li(t0, 0xc0000000)          # kernel memory from user mode
+        user.load(2, t1, t0, 0)
+    fault_pc = PF.USER_START_ADDR + 4 + 4 * (len(user.text) - 1)
+    user.ecall()                         # never reached
+    uentry, uimage = user.program()
+    kern = PF.Assembler(base=PF.KERNEL_START_ADDR)
+    kern.li(t1, uentry - 4)
+    kern.li(t0, PF.MEPC_ADDR)
+    kern.sw(t1, t0, 0)
+    kern.mret()
+    handler = PF.KERNEL_START_ADDR + 0x100
+    while PF.KERNEL_START_ADDR + 4 * len(kern.text) < handler:
+        kern.text.append(0x00000013)
+    kern.li(t0, PF.MEPC_ADDR)
+    kern.load(2, PF.REG_A0, t0, 0)       # exit code a0 = MEPC, a1 = 0
+    kern.li(PF.REG_A7, PF.HOST_ECALL_TERMINATE)
+    kern.li(PF.REG_A1, 0)
+    kern.ecall()
+    kentry, kimage = kern.program()
+    image = dict(uimage)
+    image.update(kimage)
+    image[PF.ECALL_DISPATCH_ADDR] = PF.KERNEL_START_ADDR + 0x80      # a user ecall would land in the nops, not the handler
+    for cause in range(12):
+        image[PF.TRAP_DISPATCH_ADDR + 4 * cause] = handler
+    segs = PF.execute(PF.MemoryImage.new_kernel(kentry, image), segment_po2=14)
+    assert len(segs) == 1 and segs[0].terminate_state == (fault_pc, 0)
+    pf = PF.PreflightResults(segs[0], (1, 2, 3, 4))
+    with pytest.raises(RuntimeError):
+        W.host_generate_witness(pf)
+
+
 def test_input_output_digests_and_exit_codes():
     """a guest that reads its input digest, writes an output digest and terminates with (a0, a1) = (2, 7): the witness
     generator's output globals (output, termA0 / termA1, stateOut) come out as the executor's claim says"""
