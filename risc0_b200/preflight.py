@@ -2342,3 +2342,55 @@ def poseidon2_ecall_guest(words, is_elem, state=None, expect=None):
     asm.host_terminate(0, 0)
     entry, image = asm.program()
     return MemoryImage.new_kernel(entry, image)
+
+
+def user_sha2_via_kernel_guest(message=b"abc"):
+    """the production shape of an accelerator call (zkos/v1compat/src/kernel.s:60-100,190-240): a USER-mode program puts
+    the arguments in its registers and executes `ecall`; the machine-mode kernel's dispatch handler reads them out of the
+    user register file (plain memory at USER_REGS_ADDR), issues the machine ecall - sha2 here - and `mret`s back; a second
+    user ecall with a7 = 0 makes the kernel terminate. The digest lands at SHA2_GUEST_OUT_ADDR."""
+    t0, t1 = 5, 6
+    data_addr, state_addr, k_addr = 0x00500000, 0x00500300, 0x00500500
+    ml = len(message)
+    padded = bytes(message) + b"\x80" + b"\x00" * ((55 - ml) % 64) + (8 * ml).to_bytes(8, "big")
+    user = Assembler()
+    for i in range(len(padded) // 4):
+        user.word(data_addr + 4 * i, int.from_bytes(padded[4 * i:4 * i + 4], "little"))
+    for i, w in enumerate(SHA256_IV):
+        user.word(state_addr + 4 * i, _bswap(w))
+    for i, w in enumerate(SHA256_K):
+        user.word(k_addr + 4 * i, w)
+    user.li(REG_A0, state_addr)
+    user.li(REG_A1, SHA2_GUEST_OUT_ADDR)
+    user.li(REG_A2, data_addr)
+    user.li(REG_A3, len(padded) // 64)
+    user.li(REG_A4, k_addr)
+    user.li(REG_A7, 1)                  # "hash"
+    user.ecall()
+    user.li(t0, SHA2_GUEST_OUT_ADDR)
+    user.load(2, t1, t0, 0)             # back in user mode: read the digest
+    user.li(REG_A7, 0)                  # "exit"
+    user.ecall()
+    uentry, uimage = user.program()
+    kern = Assembler(base=KERNEL_START_ADDR)
+    kern.li(t1, uentry - 4)             # mret resumes at MEPC + 4
+    kern.li(t0, MEPC_ADDR)
+    kern.sw(t1, t0, 0)
+    kern.mret()
+    handler = KERNEL_START_ADDR + 0x100
+    while KERNEL_START_ADDR + 4 * len(kern.text) < handler:
+        kern.text.append(0x00000013)
+    kern.li(t0, USER_REGS_ADDR)
+    kern.load(2, t1, t0, 4 * REG_A7)
+    kern.beq(t1, 0, 4 * 9)              # a7 == 0 -> the terminate sequence after the 8 instructions below
+    for r in (REG_A0, REG_A1, REG_A2, REG_A3, REG_A4):
+        kern.load(2, r, t0, 4 * r)
+    kern.addi(REG_A7, 0, HOST_ECALL_SHA2)
+    kern.ecall()
+    kern.mret()
+    kern.host_terminate(0, 0)
+    kentry, kimage = kern.program()
+    image = dict(uimage)
+    image.update(kimage)
+    image[ECALL_DISPATCH_ADDR] = handler
+    return MemoryImage.new_kernel(kentry, image)

@@ -28,6 +28,7 @@ def segments():
     out["sha2"] = PF.execute(PF.sha2_guest(bytes(range(200))), segment_po2=14)[0]   # 4 blocks through the sha2 ecall
     out["bigint"] = PF.execute(bigint_guest(2)[0], segment_po2=14)[0]               # modmul_256 through the bigint ecall
     out["host_write"] = PF.execute(host_write_guest(), segment_po2=14)[0]
+    out["user_sha2"] = PF.execute(PF.user_sha2_via_kernel_guest(bytes(range(70))), segment_po2=14)[0]   # user -> kernel -> sha2
     rng = np.random.default_rng(77)                                                  # guest-invoked poseidon2 ecall with state
     out["p2_ecall"] = PF.execute(PF.poseidon2_ecall_guest([int(x) for x in rng.integers(0, 1 << 32, 24)], 0,
                                                           [int(x) for x in rng.integers(0, PF.P, 8)]), segment_po2=14)[0]
@@ -47,7 +48,7 @@ def seg(name):
 
 
 @pytest.mark.parametrize("name", ["loop_po2_13", "all_insn", "split_first", "split_second", "user_mode", "sha2", "bigint",
-                                  "p2_ecall", "host_write"])
+                                  "p2_ecall", "host_write", "user_sha2"])
 def test_device_witgen_and_accum_match_reference(hal, name):
     # (host_write: with the write record indexed as the executor wrote it, see tests/test_preflight.py::test_host_write_guest)
     pf = PF.PreflightResults(seg(name), (11, 12, 13, 14), write_record_off_by_one=name != "host_write")

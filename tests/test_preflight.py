@@ -129,6 +129,24 @@ def all_insn_guest():
     return PF.MemoryImage.new_kernel(entry, image)
 
 
+def test_user_program_calls_sha2_through_the_kernel():
+    """the production shape of an accelerator call (zkos/v1compat/src/kernel.s): user `ecall` -> kernel dispatch reads the
+    user register file -> machine sha2 ecall -> `mret` -> user code reads the digest -> second ecall -> kernel terminates"""
+    import hashlib
+    msg = bytes(range(70))
+    segs = PF.execute(PF.user_sha2_via_kernel_guest(msg), segment_po2=14)
+    assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
+    pf, _, _, _ = check_segment(segs[0], seed=14)
+    kinds = list(zip(pf.cycles["major"].tolist(), pf.cycles["minor"].tolist()))
+    assert kinds.count((7, 2)) >= 2 and kinds.count((7, 3)) == 2 and kinds.count((11, 3)) == 96   # 2 user ecalls, 2 mrets, 2 blocks
+    out = {}
+    for t in pf.txns:
+        addr = int(t["addr"]) * 4
+        if PF.SHA2_GUEST_OUT_ADDR <= addr < PF.SHA2_GUEST_OUT_ADDR + 32 and int(t["cycle"]) % 2 == 1:
+            out[addr] = int(t["word"])
+    assert b"".join(out[PF.SHA2_GUEST_OUT_ADDR + 4 * i].to_bytes(4, "little") for i in range(8)) == hashlib.sha256(msg).digest()
+
+
 @pytest.mark.parametrize("kind", ["illegal", "misaligned_load", "misaligned_store", "load_fault"])
 def test_user_traps_reach_the_kernel_handler(kind):
     """executor only: a user-mode fault enters the kernel through TRAP_DISPATCH_ADDR[cause] with MEPC = the faulting pc
