@@ -26,7 +26,7 @@ def ints(s):
 shutil.copyfile(os.path.join(REF, "risc0/zkp/src/verify/proof.bin"), os.path.join(HERE, "proof.bin"))
 # bigint2 programs (blob = header + bibc 'nondet' program + verify program + constants) that the bigint-ecall guests of
 # tests/test_preflight.py / tests/test_gpu_witgen.py run: risc0/bigint2/src/field/<name>.blob -> bigint_<name>.blob
-for name in ("modmul_256", "modinv_256", "modsub_256", "modadd_256", "modmul_384", "extfield_deg2_mul_256"):
+for name in ("modmul_256", "modinv_256", "modsub_256", "modadd_256", "modmul_384", "extfield_deg2_mul_256", "modmul_4096"):
     shutil.copyfile(os.path.join(REF, "risc0/bigint2/src/field/%s.blob" % name), os.path.join(HERE, "bigint_%s.blob" % name))
 
 bb = read("risc0/core/src/field/baby_bear.rs")

@@ -432,7 +432,7 @@ P256 = 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff
 P384 = 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffeffffffff0000000000000000ffffffff
 
 
-@pytest.mark.parametrize("name", ["modinv_256", "modsub_256", "modadd_256", "modmul_384", "extfield_deg2_mul_256"])
+@pytest.mark.parametrize("name", ["modinv_256", "modsub_256", "modadd_256", "modmul_384", "extfield_deg2_mul_256", "modmul_4096"])
 def test_bigint_blobs_of_the_reference(name):
     """more of the reference's bigint2 field programs (risc0/bigint2/src/field/*.blob, copied as fixtures): Inv and the
     constants section (modinv), negative intermediates (modsub), 384-bit operands = three chunks per value (modmul_384), a
@@ -451,6 +451,11 @@ def test_bigint_blobs_of_the_reference(name):
         a, b = rnd(P256), rnd(P256)
         inputs = {A1: a.to_bytes(32, "little"), A2: b.to_bytes(32, "little"), A3: P256.to_bytes(32, "little")}
         outputs, want = {A4: 32}, ((a - b) if name == "modsub_256" else (a + b)) % P256
+    elif name == "modmul_4096":      # the RSA-sized program: 485 verify-program words, 32 chunks per operand
+        n = int.from_bytes(rng.bytes(512), "little") | (1 << 4095) | 1
+        a, b = int.from_bytes(rng.bytes(512), "little") % n, int.from_bytes(rng.bytes(512), "little") % n
+        inputs = {A1: a.to_bytes(512, "little"), A2: b.to_bytes(512, "little"), A3: n.to_bytes(512, "little")}
+        outputs, want = {A4: 512}, a * b % n
     elif name == "modmul_384":
         a, b = rnd(P384), rnd(P384)
         inputs = {A1: a.to_bytes(48, "little"), A2: b.to_bytes(48, "little"), A3: P384.to_bytes(48, "little")}
