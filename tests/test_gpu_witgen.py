@@ -9,7 +9,7 @@ import oracle_lib as O
 import witgen_ref as W
 from risc0_b200 import B200Hal, SegmentProver, WitnessGenerator
 from risc0_b200 import preflight as PF
-from test_preflight import all_insn_guest, bigint_guest, host_write_guest
+from test_preflight import all_insn_guest, host_write_guest, modmul_guest
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (W.have_ref() and O.have_ref()), reason="oracle/_ref not built")]
 
@@ -26,7 +26,7 @@ def segments():
            "all_insn": PF.execute(all_insn_guest(), segment_po2=14)[0]}
     out["user_mode"] = PF.execute(PF.user_mode_guest(30), segment_po2=14)[0]
     out["sha2"] = PF.execute(PF.sha2_guest(bytes(range(200))), segment_po2=14)[0]   # 4 blocks through the sha2 ecall
-    out["bigint"] = PF.execute(bigint_guest(2)[0], segment_po2=14)[0]               # modmul_256 through the bigint ecall
+    out["bigint"] = PF.execute(modmul_guest(2)[0], segment_po2=14)[0]               # modmul_256 through the bigint ecall
     out["host_write"] = PF.execute(host_write_guest(), segment_po2=14)[0]
     out["user_sha2"] = PF.execute(PF.user_sha2_via_kernel_guest(bytes(range(70))), segment_po2=14)[0]   # user -> kernel -> sha2
     rng = np.random.default_rng(77)                                                  # guest-invoked poseidon2 ecall with state

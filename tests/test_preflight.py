@@ -379,7 +379,7 @@ def test_sha2_ecall_guest(message):
     assert digest == hashlib.sha256(message).digest()
 
 
-def bigint_guest(seed=0):
+def modmul_guest(seed=0):
     """modmul_256 from the reference's bigint2 crate (tests/golden/bigint_modmul_256.blob = risc0/bigint2/src/field/
     modmul_256.blob, a reference-held fixture) on the secp256k1 prime"""
     import os
@@ -397,7 +397,7 @@ def test_bigint_ecall_guest(seed):
     cycles, the 16 witness bytes per cycle) and the generated step functions reproduce it; with the BigIntAccumState cells
     computed from the mix (witgen/mod.rs:186-207) the reference accum runs and EVERY constraint holds - including the
     bigint accumulator's own polynomial identity at the mix point."""
-    image, (a, b, n) = bigint_guest(seed)
+    image, (a, b, n) = modmul_guest(seed)
     segs = PF.execute(image, segment_po2=14)
     assert len(segs) == 1 and segs[0].terminate_state == (0, 0)
     pf, _, _, _ = check_segment(segs[0], seed=6)
