@@ -2217,7 +2217,7 @@ SHA256_IV = [0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b056
 SHA2_GUEST_OUT_ADDR = 0x00500400
 
 
-def sha2_guest(message=b"abc", loops=3):
+def sha2_guest(message=b"abc", loops=3, repeat=1):
     """machine-mode guest that hashes `message` with the sha2 ecall (r0vm.rs:559-571, execute/sha2.rs): the padded
     message's blocks, the SHA-256 initial state (big-endian words, as the ecall reads them) and the round-constant table
     live in guest memory; the digest lands at SHA2_GUEST_OUT_ADDR as 32 bytes in digest order. A short loop before and a
@@ -2238,13 +2238,14 @@ def sha2_guest(message=b"abc", loops=3):
     asm.li(a5, loops)
     asm.addi(a4, a4, 1)
     asm.blt(a4, a5, -4)
-    asm.li(REG_A0, state_addr)
-    asm.li(REG_A1, SHA2_GUEST_OUT_ADDR)
-    asm.li(REG_A2, data_addr)
-    asm.li(REG_A3, len(padded) // 64)
-    asm.li(REG_A4, k_addr)
-    asm.li(REG_A7, HOST_ECALL_SHA2)
-    asm.ecall()
+    for _ in range(repeat):              # repeat > 1: the same hash again and again (long sessions that split)
+        asm.li(REG_A0, state_addr)
+        asm.li(REG_A1, SHA2_GUEST_OUT_ADDR)
+        asm.li(REG_A2, data_addr)
+        asm.li(REG_A3, len(padded) // 64)
+        asm.li(REG_A4, k_addr)
+        asm.li(REG_A7, HOST_ECALL_SHA2)
+        asm.ecall()
     asm.li(t3, SHA2_GUEST_OUT_ADDR)
     asm.load(2, a4, t3, 0)               # lw: the stored state is read back by an ordinary instruction
     asm.load(2, a5, t3, 28)

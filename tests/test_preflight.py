@@ -491,6 +491,26 @@ def test_bigint_accum_columns():
     assert re.search(r"kBigIntAccumCols\[3\] = \{0, 4, 8\}", src) and "kMajorBigInt = 12" in src
 
 
+def test_sha2_session_splits_between_ecalls():
+    """40 ten-block hashes in a row at a small segment size: the executor may only cut between instructions (an ecall's
+    cycles stay together), every segment re-pages the message / round constants / state it touches, and each one is
+    accepted by the reference's witgen"""
+    import hashlib
+    msg = bytes((7 * i) & 0xff for i in range(575))
+    segs = PF.execute(PF.sha2_guest(msg, repeat=40), segment_po2=14)
+    assert len(segs) >= 3 and segs[-1].terminate_state == (0, 0)
+    for sg in segs:
+        pf, _, _, _ = check_segment(sg, seed=15)
+        kinds = list(zip(pf.cycles["major"].tolist(), pf.cycles["minor"].tolist()))
+        assert kinds.count((11, 3)) % 480 == 0        # whole ecalls only: 48 mix cycles x 10 blocks each
+    out = {}
+    for t in pf.txns:
+        addr = int(t["addr"]) * 4
+        if PF.SHA2_GUEST_OUT_ADDR <= addr < PF.SHA2_GUEST_OUT_ADDR + 32 and int(t["cycle"]) % 2 == 1:
+            out[addr] = int(t["word"])
+    assert b"".join(out[PF.SHA2_GUEST_OUT_ADDR + 4 * i].to_bytes(4, "little") for i in range(8)) == hashlib.sha256(msg).digest()
+
+
 def _p2_sponge(words, is_elem, state):
     cells = [0] * 24
     if state is not None:
